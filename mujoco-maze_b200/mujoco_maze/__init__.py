@@ -1,0 +1,68 @@
+"""mujoco_maze — B200-native batched maze-navigation environments.
+
+Same user-facing surface as kngwyu/mujoco-maze (reference mujoco_maze/__init__.py:
+importing the package registers `Point/Ant/Swimmer{Maze}-v{i}` with entry point
+`mujoco_maze.maze_env:MazeEnv`), but `MazeEnv.step` advances N lock-step
+environments in one hand-written sm_100a CUDA kernel behind the C ABI of
+include/mmz.h. `gym` is used when installed; otherwise `mujoco_maze.gym` is a
+minimal in-repo shim of the slice of gym 0.20 the API needs.
+"""
+
+try:  # pragma: no cover - gym is absent in the build image
+    import gym  # type: ignore
+
+    if not hasattr(gym, "envs") or not hasattr(gym.envs, "register"):
+        raise ImportError
+except ImportError:
+    from mujoco_maze import gym_shim as gym  # noqa: F401
+
+from mujoco_maze.ant import AntEnv  # noqa: E402
+from mujoco_maze.maze_task import TaskRegistry  # noqa: E402
+from mujoco_maze.point import PointEnv  # noqa: E402
+from mujoco_maze.swimmer import SwimmerEnv  # noqa: E402
+
+__version__ = "0.2.0+b200.r1"
+
+MAX_EPISODE_STEPS = 1000  # reference __init__.py:31,47,76
+
+_AGENTS = (  # (id prefix, descriptor class, which Scaling field selects the maze size)
+    ("Point", PointEnv, "point"),
+    ("Ant", AntEnv, "ant"),
+    ("Swimmer", SwimmerEnv, "swimmer"),
+)
+# ReacherEnv (reference __init__.py:51-64, "not tested" per README.md:129-130) is out of
+# scope of the hot path this package rebuilds; its ids are intentionally not registered.
+
+
+def _register_all() -> None:
+    for maze_id in TaskRegistry.keys():
+        for version, task_cls in enumerate(TaskRegistry.tasks(maze_id)):
+            for prefix, agent_cls, scale_field in _AGENTS:
+                scale = getattr(task_cls.MAZE_SIZE_SCALING, scale_field)
+                if scale is None:
+                    continue
+                env_id = f"{prefix}{maze_id}-v{version}"
+                if env_id in getattr(gym.envs.registry, "env_specs", {}):
+                    continue  # re-import
+                gym.envs.register(
+                    id=env_id,
+                    entry_point="mujoco_maze.maze_env:MazeEnv",
+                    kwargs=dict(
+                        model_cls=agent_cls,
+                        maze_task=task_cls,
+                        maze_size_scaling=scale,
+                        inner_reward_scaling=task_cls.INNER_REWARD_SCALING,
+                    ),
+                    max_episode_steps=MAX_EPISODE_STEPS,
+                    reward_threshold=task_cls.REWARD_THRESHOLD,
+                )
+
+
+_register_all()
+
+
+def install_gym_shim() -> None:
+    """Expose the in-repo shim as `import gym` when the real package is missing."""
+    import sys
+
+    sys.modules.setdefault("gym", gym)

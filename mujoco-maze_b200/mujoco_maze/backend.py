@@ -1,0 +1,191 @@
+"""ctypes binding of libmmz.so (include/mmz.h) over PyTorch device memory.
+
+PyTorch is used for device allocations, streams and (optionally)
+torch.distributed; every computation of the step path happens inside the CUDA
+library. There is NO CPU fallback: if the library is missing or CUDA is not
+available this module raises — the hot path must never silently run elsewhere.
+"""
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_ROOT, "libmmz.so")
+
+MMZ_DONE, MMZ_TRUNCATED, MMZ_UNSTABLE = 1, 2, 4
+MMZ_AUTO_RESET = 1
+LAYOUT_ENV_MAJOR, LAYOUT_SOA = 0, 1
+ABI_VERSION = 1
+
+_lib = None
+
+
+class MmzError(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """dlopen libmmz.so and declare the signatures of include/mmz.h."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise MmzError(
+            f"{path} not found: the CUDA extension is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
+            "There is no CPU fallback for the step path."
+        )
+    lib = ctypes.CDLL(path)
+    vp, i32, u32, u64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_size_t
+    ip = ctypes.POINTER(ctypes.c_int)
+    sig = {
+        "mmz_create": ([vp, sz, i32, i32, u32, ctypes.POINTER(vp)], i32),
+        "mmz_dims": ([vp, ip, ip, ip, ip, ip], i32),
+        "mmz_reset": ([vp, vp, u64, vp, vp], i32),
+        "mmz_step": ([vp, vp, vp, vp, vp, vp, vp], i32),
+        "mmz_step_host": ([vp, vp, vp, vp, vp, vp, vp], i32),
+        "mmz_observe": ([vp, vp, vp], i32),
+        "mmz_get_state": ([vp, i32, vp, vp, vp, vp], i32),
+        "mmz_set_state": ([vp, i32, vp, vp, vp, vp], i32),
+        "mmz_forward": ([vp, vp, vp, vp, vp], i32),
+        "mmz_launch_count": ([vp], u64),
+        "mmz_last_error": ([], ctypes.c_char_p),
+        "mmz_destroy": ([vp], None),
+        "mmz_abi_version": ([], i32),
+    }
+    for name, (argtypes, restype) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.argtypes, fn.restype = argtypes, restype
+    if lib.mmz_abi_version() != ABI_VERSION:
+        raise MmzError(f"libmmz ABI {lib.mmz_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = (
+    "mmz_create", "mmz_dims", "mmz_reset", "mmz_step", "mmz_step_host", "mmz_observe", "mmz_get_state",
+    "mmz_set_state", "mmz_forward", "mmz_launch_count", "mmz_last_error", "mmz_destroy", "mmz_abi_version",
+)
+
+
+def _ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class BatchedSim:
+    """N lock-step environments on one CUDA device (one `mmz_handle`)."""
+
+    def __init__(self, model, num_envs: int, device="cuda:0", auto_reset: bool = False):
+        import torch
+
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise MmzError("CUDA is not available: the maze step path is GPU-only (no CPU fallback)")
+        self.lib = load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise MmzError(f"device must be a CUDA device, got {device}")
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.model = model
+        self.n = int(num_envs)
+        blob = model.blob(4)
+        self._h = ctypes.c_void_p()
+        flags = MMZ_AUTO_RESET if auto_reset else 0
+        self._check(self.lib.mmz_create(blob, len(blob), self.n, self.index, flags, ctypes.byref(self._h)))
+        dims = [ctypes.c_int() for _ in range(5)]
+        self._check(self.lib.mmz_dims(self._h, *[ctypes.byref(d) for d in dims]))
+        _, self.nq, self.nv, self.nu, self.obs_dim = (d.value for d in dims)
+        dev = self.device
+        self.obs = torch.empty((self.n, self.obs_dim), dtype=torch.float32, device=dev)
+        self.reward = torch.empty((self.n,), dtype=torch.float32, device=dev)
+        self.done = torch.empty((self.n,), dtype=torch.uint8, device=dev)
+        self.info = torch.empty((self.n, 4), dtype=torch.float32, device=dev)
+
+    # -- helpers -------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise MmzError(f"libmmz error {rc}: {self.lib.mmz_last_error().decode()}")
+
+    def _stream(self) -> int:
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _f32(self, x, shape) -> "torch.Tensor":
+        t = self.torch.as_tensor(x, dtype=self.torch.float32, device=self.device).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    # -- API -----------------------------------------------------------------
+    def reset(self, seed: int = 0, mask=None):
+        m = None
+        if mask is not None:
+            m = self.torch.as_tensor(mask, device=self.device).to(self.torch.uint8).contiguous()
+        self._check(self.lib.mmz_reset(self._h, _ptr(m), int(seed), self.obs.data_ptr(), self._stream()))
+        return self.obs
+
+    def step(self, action):
+        a = self._f32(action, (self.n, self.nu))
+        self._check(self.lib.mmz_step(self._h, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
+                                      self.done.data_ptr(), self.info.data_ptr(), self._stream()))
+        return self.obs, self.reward, self.done, self.info
+
+    def step_into(self, action, obs, reward, done, info=None):
+        """Step with caller-provided output tensors (bench / multi-buffering)."""
+        self._check(self.lib.mmz_step(self._h, action.data_ptr(), obs.data_ptr(), reward.data_ptr(),
+                                      done.data_ptr(), _ptr(info), self._stream()))
+
+    def step_host(self, h_action, h_obs, h_reward, h_done, h_info=None):
+        """End-to-end step through pinned host tensors (synchronises the stream)."""
+        self._check(self.lib.mmz_step_host(self._h, h_action.data_ptr(), h_obs.data_ptr(), h_reward.data_ptr(),
+                                           h_done.data_ptr(), _ptr(h_info), self._stream()))
+
+    def observe(self):
+        self._check(self.lib.mmz_observe(self._h, self.obs.data_ptr(), self._stream()))
+        return self.obs
+
+    def get_state(self, layout: int = LAYOUT_ENV_MAJOR):
+        t = self.torch
+        shape_q = (self.n, self.nq) if layout == LAYOUT_ENV_MAJOR else (self.nq, self.n)
+        shape_v = (self.n, self.nv) if layout == LAYOUT_ENV_MAJOR else (self.nv, self.n)
+        qpos = t.empty(shape_q, dtype=t.float32, device=self.device)
+        qvel = t.empty(shape_v, dtype=t.float32, device=self.device)
+        step = t.empty((self.n,), dtype=t.int32, device=self.device)
+        self._check(self.lib.mmz_get_state(self._h, layout, qpos.data_ptr(), qvel.data_ptr(), step.data_ptr(),
+                                           self._stream()))
+        return qpos, qvel, step
+
+    def set_state(self, qpos=None, qvel=None, t=None, layout: int = LAYOUT_ENV_MAJOR):
+        shape_q = (self.n, self.nq) if layout == LAYOUT_ENV_MAJOR else (self.nq, self.n)
+        shape_v = (self.n, self.nv) if layout == LAYOUT_ENV_MAJOR else (self.nv, self.n)
+        q = None if qpos is None else self._f32(qpos, shape_q)
+        v = None if qvel is None else self._f32(qvel, shape_v)
+        s = None if t is None else self.torch.as_tensor(t, dtype=self.torch.int32, device=self.device).contiguous()
+        self._check(self.lib.mmz_set_state(self._h, layout, _ptr(q), _ptr(v), _ptr(s), self._stream()))
+
+    def forward(self, action) -> Tuple["torch.Tensor", "torch.Tensor"]:
+        t = self.torch
+        a = self._f32(action, (self.n, self.nu))
+        qacc = t.empty((self.n, self.nv), dtype=t.float32, device=self.device)
+        diag = t.empty((self.n, 4), dtype=t.int32, device=self.device)
+        self._check(self.lib.mmz_forward(self._h, a.data_ptr(), qacc.data_ptr(), diag.data_ptr(), self._stream()))
+        return qacc, diag
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mmz_launch_count(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.mmz_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
