@@ -718,7 +718,7 @@ def compile_maze_model(
         sc_m, flat = sc, flat_full
         geom_src = list(flat_full["geom_body"])
     names = flat.pop("_names")
-    flat_full.pop("_names")
+    flat_full.pop("_names", None)
     assert flat["nv"] == flat_full["nv"] and np.allclose(flat["qpos0"], flat_full["qpos0"])
     for cap, key in (("MAXBODY", "nbody"), ("MAXJNT", "njnt"), ("MAXDOF", "nv"), ("MAXQ", "nq"), ("MAXGEOM", "ngeom")):
         if flat[key] > L.CAPS[cap]:
