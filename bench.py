@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py - env steps/s of the fused MazeEnv.step kernel, beside the CPU restatement.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ID:NENVS] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one MazeEnv.step over one batch of N_envs lock-step environments (per GPU). The default
+workload is the configuration BASELINE.json's north-star target is quoted on: AntUMaze-v0 at 65 536
+parallel environments per B200 (configs[2]); environments shard across ranks with no data-path
+collective (weak scaling). Prints ONE JSON line (rank 0).
+
+  value     whole-job env steps/s, inputs (actions) already resident in HBM, CUDA-event timed per
+            step on the launching stream, L2 flushed between timed steps, max over ranks
+  e2e       same metric through the C-ABI host call (mmz_step_host): pinned-host actions in,
+            obs/reward/done/info out, copies inside the timed region
+  roofline  algorithmic HBM bytes of one launch / its average duration vs the measured copy peak
+  cpu_baseline  the fp64 CPU restatement (oracle/, "port": mujoco-py is not installable here)
+            timed on this box's host cores on a bounded sample of the same workload (rank 0, N=1)
+  --impl reference  times that CPU restatement alone, all host threads, same config and metric
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "mujoco-maze_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="AntUMaze-v0:65536", help="ENV_ID:ENVS_PER_GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gather-obs", action="store_true", help="all-gather the observations over NCCL inside the step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--ref-envs", type=int, default=0, help="--impl reference: environments per step (0 = auto)")
+    return ap.parse_args()
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def make_model(env_id):
+    import mujoco_maze  # noqa: F401
+    from mujoco_maze import gym
+
+    return gym.make(env_id).unwrapped.model
+
+
+def initial_state(model, n, seed):
+    """reset_model distributions (ant.py:84-96 / point.py:71-81 / swimmer.py:55-68) in numpy, for the CPU legs."""
+    rng = np.random.default_rng(seed)
+    nq, nv = int(model.nq), int(model.nv)
+    naq, nav = int(model.n_agent_q), int(model.n_agent_v)
+    q = np.tile(np.asarray(model.qpos0, float)[:nq], (n, 1))
+    v = np.zeros((n, nv))
+    q[:, :naq] += rng.uniform(-0.1, 0.1, size=(n, naq))
+    kind = int(model.reset_kind)
+    if kind == 0:
+        v[:, :nav] = 0.1 * rng.random((n, nav))
+    elif kind == 1:
+        v[:, :nav] = 0.1 * rng.normal(size=(n, nav))
+    else:
+        v[:, :nav] = rng.uniform(-0.1, 0.1, size=(n, nav))
+    return q, v
+
+
+def action_bounds(model):
+    r = np.asarray(model.meta["act_ctrlrange"], float)
+    return r[:, 0], r[:, 1]
+
+
+def time_cpu(model, n_envs, steps, warmup, threads, seed=0):
+    """steps/s of the CPU restatement on `threads` host threads over n_envs persistent environments."""
+    from oracle import mmz_oracle
+
+    lo, hi = action_bounds(model)
+    rng = np.random.default_rng(seed + 1)
+    batch = mmz_oracle.OracleBatch(model, n_envs)
+    q, v = initial_state(model, n_envs, seed)
+    batch.set_state(q, v)
+    acts = [rng.uniform(lo, hi, size=(n_envs, len(lo))) for _ in range(min(8, warmup + steps))]
+    for s in range(warmup):
+        batch.step(acts[s % len(acts)], threads)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        batch.step(acts[(warmup + s) % len(acts)], threads)
+    dt = time.perf_counter() - t0
+    batch.close()
+    return n_envs * steps / dt, dt
+
+
+def cpu_baseline(model, env_id, target_seconds):
+    cores = host_cores()
+    probe_envs = 8 * cores
+    rate, _ = time_cpu(model, probe_envs, 2, 1, cores)
+    steps = 10
+    n_envs = int(max(probe_envs, min(65536, rate * target_seconds / steps)))
+    n_envs = max(cores, n_envs // cores * cores)
+    value, dt = time_cpu(model, n_envs, steps, 2, cores)
+    return {
+        "value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{n_envs} {env_id} envs x {steps} steps after 2 warm-up steps ({dt:.1f} s), fp64 CPU restatement "
+                  f"(oracle/mmz_oracle.c, OpenMP); mujoco-py / MuJoCo are not installable in this image",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes_per_env_step(model, with_info=True):
+    """HBM bytes one env-step must move: persisted state rows read + written, action in, obs/reward/done(/info) out.
+
+    State rows: qpos, qvel, qacc (solver warm start), 3 per observed body; counters t and n_reset (int32)."""
+    rows = int(model.nq) + 2 * int(model.nv) + 3 * int(model.nobj)
+    b = 2 * 4 * rows + 2 * 2 * 4 + 4 * int(model.nu) + 4 * int(model.obs_dim) + 4 + 1
+    return b + (16 if with_info else 0)
+
+
+def run_reference(args, env_id, n_envs):
+    """The reference arm: the CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model = make_model(env_id)
+    cores = host_cores()
+    if args.ref_envs:
+        sample = args.ref_envs
+    else:
+        rate, _ = time_cpu(model, 8 * cores, 2, 1, cores)
+        budget = 150.0  # seconds for the whole run
+        sample = int(rate * budget / max(1, args.steps + args.warmup))
+        sample = max(cores, min(n_envs, sample) // cores * cores)
+    value, dt = time_cpu(model, sample, args.steps, args.warmup, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{env_id}, {n_envs} parallel envs per GPU", "sample_envs_per_step": sample,
+                   "note": "reference arm = fp64 CPU restatement of MazeEnv.step (oracle/); the reference's own "
+                           "mujoco-py loop cannot be installed here (closed MuJoCo 2.0 binary, no network)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} envs per step x {args.steps} steps, OpenMP {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    env_id, n_envs = args.workload.split(":")
+    n_envs = int(n_envs)
+    if args.impl == "reference":
+        run_reference(args, env_id, n_envs)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from mujoco_maze.backend import BatchedSim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    model = make_model(env_id)
+    sim = BatchedSim(model, n_envs, dev, auto_reset=True, env_offset=rank * n_envs)
+    nu, od = sim.nu, sim.obs_dim
+    lo, hi = action_bounds(model)
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    lo_t, hi_t = torch.tensor(lo, device=dev, dtype=torch.float32), torch.tensor(hi, device=dev, dtype=torch.float32)
+    acts = [lo_t + (hi_t - lo_t) * torch.rand((n_envs, nu), generator=gen, device=dev) for _ in range(8)]
+    obs = torch.empty((n_envs, od), device=dev)
+    rew = torch.empty((n_envs,), device=dev)
+    done = torch.empty((n_envs,), device=dev, dtype=torch.uint8)
+    info = torch.empty((n_envs, 4), device=dev)
+    gathered = torch.empty((world * n_envs, od), device=dev) if (args.gather_obs and world > 1) else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def one_step(i):
+        sim.step_into(acts[i % len(acts)], obs, rew, done, info)
+        if gathered is not None:
+            dist.all_gather_into_tensor(gathered, obs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sim.reset(seed=0)
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+
+    # ---- device-resident timing: one CUDA-event pair per step, L2 flushed between steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = sim.launch_count
+    done_frac = 0.0
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        one_step(args.warmup + i)
+        ends[i].record()
+    barrier()
+    launches = sim.launch_count - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    done_frac = float((done & 1).float().mean().item())
+    unstable = int(((done & 4) != 0).sum().item())
+
+    # ---- end to end through the C-ABI host call: pinned host buffers, copies inside the timed region
+    h_acts = [a.cpu().pin_memory() for a in acts[:4]]
+    h_obs = torch.empty((n_envs, od), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty((n_envs,), dtype=torch.float32).pin_memory()
+    h_done = torch.empty((n_envs,), dtype=torch.uint8).pin_memory()
+    h_info = torch.empty((n_envs, 4), dtype=torch.float32).pin_memory()
+    e2e_steps = max(5, args.steps // 2)
+    for i in range(3):
+        sim.step_host(h_acts[i % 4], h_obs, h_rew, h_done, h_info)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        sim.step_host(h_acts[i % 4], h_obs, h_rew, h_done, h_info)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            with open(peaks_path) as f:
+                peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+        ms_per_step = total_ms / args.steps
+        bytes_per_launch = algorithmic_bytes_per_env_step(model) * n_envs
+        achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # written from an ncu --set full capture
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(args.workload)
+        line = {
+            "metric": METRIC, "value": world * n_envs * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{env_id}, {n_envs} parallel envs per GPU", "frame_skip": int(model.frame_skip),
+                       "integrator": "RK4", "auto_reset": True, "l2": "flushed (256 MiB write) between timed steps",
+                       "actions": "pre-generated on device, uniform over ctrlrange", "gather_obs": gathered is not None,
+                       "kernel": sim.kernel_config, "done_frac_last_step": done_frac, "unstable_last_step": unstable},
+            "clocks": clocks,
+            "e2e": {"value": world * n_envs * e2e_steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": n_envs * nu * 4, "d2h_bytes_per_step": n_envs * (od * 4 + 4 + 1 + 16),
+                    "steps": e2e_steps, "api": "mmz_step_host (C ABI, pinned host buffers, synchronous)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_env_step": algorithmic_bytes_per_env_step(model),
+                         "kernel": "maze_kernel<G,NVP,MODE_STEP>",
+                         "note": "nominal bound; the step is fp32-issue / latency bound (about 1 MFLOP per Ant env-step "
+                                 "against 0.5 KB of HBM traffic), see DESIGN.md"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(model, env_id, args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,19 @@ int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, u
 /* Sizes implied by the model. Any out pointer may be NULL. */
 int mmz_dims(mmz_handle h, int* num_envs, int* nq, int* nv, int* nu, int* obs_dim);
 
+/* How the step kernel was configured for this model on this device: lanes of a warp that
+ * cooperate on one environment (8, 16 or 32 = one warp per environment), threads per block,
+ * dynamic shared memory per block, resident environments per SM and the per-environment
+ * shared-memory workspace in floats. Any out pointer may be NULL. */
+int mmz_kernel_config(mmz_handle h, int* lanes_per_env, int* threads_per_block, int* smem_bytes, int* envs_per_sm,
+                      int* floats_per_env);
+
+/* Multi-GPU sharding: this handle holds environments [first_global_env, first_global_env + N)
+ * of a larger batch. Only the reset noise depends on it (Philox streams are keyed by the GLOBAL
+ * environment index), so 1 GPU x N and G GPUs x N/G give identical results. There is no
+ * reference counterpart: the reference holds one mjData per Python object (maze_env.py:218). */
+int mmz_set_env_offset(mmz_handle h, int first_global_env);
+
 /* MazeEnv.reset (maze_env.py:371-382) + reset_model (point.py:71-81,
  * ant.py:84-96, swimmer.py:55-68) for the envs whose d_mask byte is non-zero
  * (NULL = all). Noise is Philox4x32-10 keyed by (seed, env index): the

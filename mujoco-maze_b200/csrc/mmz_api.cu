@@ -1,0 +1,418 @@
+// mmz_api.cu - C ABI of libmmz.so (include/mmz.h): handle management and kernel launches.
+//
+// Boundary notes: plain C signatures, caller-owned device pointers, every call only enqueues
+// on the given stream (except mmz_step_host / mmz_destroy), errors are negative return codes
+// with a thread-local message. No torch types, no exceptions across the boundary.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/mmz.h"
+#define MMZ_API_TU
+#include "mmz_kernels.cuh"
+
+using namespace mmz;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) return fail(MMZ_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+typedef mmz::kernel_fn kernel_fn;
+
+}  // namespace
+
+struct mmz_env {
+  int device = 0;
+  int n = 0, npad = 0;
+  unsigned flags = 0;
+  int G = 32, NVP = 20;  // kernel instance
+  int tpb = 128;         // threads per block
+  int smem_bytes = 0;
+  int envs_per_sm = 0;
+  int env_offset = 0;    // global index of env 0 (multi-GPU sharding keeps the Philox streams global)
+  Layout L;
+  mmz_model hm;          // host copy (float layout)
+  void* d_model = nullptr;
+  float* d_state = nullptr;
+  int* d_counters = nullptr;
+  // staging for mmz_step_host
+  float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_info = nullptr;
+  uint8_t* d_done = nullptr;
+  unsigned long long seed = 0;
+  unsigned long long launches = 0;
+  kernel_fn fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+void make_layout(const mmz_model& m, int G, int NVP, int maxcon, Layout* out) {
+  Layout L;
+  memset(&L, 0, sizeof L);
+  L.nb = m.nbody; L.nj = m.njnt; L.nv = m.nv; L.nq = m.nq; L.nu = m.nu; L.ng = m.ngeom; L.nobj = m.nobj;
+  L.obs_dim = m.obs_dim;
+  L.ldm = m.nv | 1;
+  L.maxcon = maxcon;
+  int nlimited = 0;
+  for (int j = 0; j < m.njnt; j++) nlimited += m.jnt_limited[j] ? 1 : 0;
+  L.maxlim = 2 * nlimited;
+  L.cstride = (C_J + 3 * m.nv) | 1;
+  L.nstate = m.nq + 2 * m.nv + 3 * m.nobj;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += n; return r; };
+  L.o_qpos = take(L.nq); L.o_qvel = take(L.nv); L.o_ctrl = take(L.nu > 0 ? L.nu : 1);
+  L.o_q0 = take(L.nq); L.o_v0 = take(L.nv); L.o_xv = take(L.nv); L.o_fa = take(L.nv);
+  L.o_accv = take(L.nv); L.o_acca = take(L.nv);
+  L.o_xpos = take(3 * L.nb); L.o_xquat = take(4 * L.nb); L.o_xmat = take(9 * L.nb);
+  L.o_xipos = take(3 * L.nb); L.o_ximat = take(9 * L.nb);
+  L.o_xanchor = take(3 * L.nj); L.o_xaxis = take(3 * L.nj);
+  L.o_gpos = take(3 * L.ng); L.o_gmat = take(9 * L.ng);
+  L.o_cdof = take(6 * L.nv);
+  L.o_iw = take(10 * L.nb);
+  // composite inertias are dead once M is built; the RNE velocity / acceleration arrays reuse them
+  L.o_ic = take(12 * L.nb); L.o_vel = L.o_ic; L.o_acc = L.o_ic + 6 * L.nb;
+  L.o_frc = take(6 * L.nb); L.o_fsub = take(6 * L.nb);
+  L.o_M = take(L.nv * L.ldm); L.o_H = take(L.nv * L.ldm);
+  L.o_bias = take(L.nv); L.o_passive = take(L.nv); L.o_smooth = take(L.nv); L.o_qacc_smooth = take(L.nv);
+  L.o_qacc = take(L.nv); L.o_grad = take(L.nv); L.o_dir = take(L.nv); L.o_tmp = take(L.nv);
+  L.o_col = take(2 * NVP);
+  L.o_con = take(L.maxcon * L.cstride);
+  L.o_lim = take((L.maxlim > 0 ? L.maxlim : 1) * R_STRIDE);
+  L.o_cnt = take(N_CNT);
+  L.o_objpos = take(3 * L.nobj > 0 ? 3 * L.nobj : 1);
+  L.o_obs = take(L.obs_dim);
+  // stride % 32 == G % 32 so that the groups of one warp fall on disjoint bank ranges
+  int stride = round_up(o, 32) + (G % 32);
+  if (stride - 32 >= o) stride -= 32;
+  L.stride = stride;
+  L.model_bytes = round_up(round_up((int)sizeof(mmz_model), 16) + (int)sizeof(Derived), 16);
+  *out = L;
+}
+
+void make_derived(const mmz_model& m, Derived* d) {
+  memset(d, 0, sizeof *d);
+  int nlev = 0;
+  for (int b = 0; b < m.nbody; b++) {
+    int mask = 0;
+    for (int a = b; a >= 0; a = m.body_parent[a]) mask |= 1 << a;
+    d->anc[b] = mask;
+    if (m.body_level[b] + 1 > nlev) nlev = m.body_level[b] + 1;
+  }
+  d->nlev = nlev;
+  for (int g = 0; g < m.ngeom; g++)
+    if (m.geom_type[g] == MMZ_GEOM_BOX) d->boxg[d->nboxg++] = g;
+}
+
+int validate(const mmz_model& m) {
+  if (m.magic != MMZ_MAGIC) return fail(MMZ_ERR_MODEL, "bad magic 0x%x", m.magic);
+  if (m.version != MMZ_VERSION) return fail(MMZ_ERR_MODEL, "blob version %d, library expects %d", m.version, MMZ_VERSION);
+  if (m.real_bytes != 4) return fail(MMZ_ERR_MODEL, "blob must use the float layout (real_bytes=4), got %d", m.real_bytes);
+  if (m.nbody < 1 || m.nbody > MMZ_MAXBODY || m.njnt < 1 || m.njnt > MMZ_MAXJNT || m.nv < 1 || m.nv > MMZ_MAXDOF ||
+      m.nq < 1 || m.nq > MMZ_MAXQ || m.ngeom < 0 || m.ngeom > MMZ_MAXGEOM || m.nu < 0 || m.nu > MMZ_MAXACT ||
+      m.ngoal < 0 || m.ngoal > MMZ_MAXGOAL || m.nseg < 0 || m.nseg > MMZ_MAXSEG || m.nobj < 0 || m.nobj > MMZ_MAXOBJ ||
+      m.grid_h * m.grid_w > MMZ_MAXCELL || m.grid_h < 1 || m.grid_w < 1)
+    return fail(MMZ_ERR_CAPACITY, "model dimensions exceed the compiled capacities");
+  if (m.obs_dim != m.n_agent_q + m.n_agent_v + 3 * m.nobj + 1 || m.obs_dim > 64)
+    return fail(MMZ_ERR_MODEL, "inconsistent obs_dim %d", m.obs_dim);
+  for (int b = 0; b < m.nbody; b++)
+    if (m.body_parent[b] >= b) return fail(MMZ_ERR_MODEL, "bodies must be ordered parents first");
+  for (int j = 0; j < m.njnt; j++)
+    if (m.jnt_type[j] == MMZ_JNT_BALL) return fail(MMZ_ERR_MODEL, "ball joints are not supported");
+  return MMZ_OK;
+}
+
+int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s) {
+  A.L = h->L;
+  A.model = h->d_model;
+  A.state = h->d_state;
+  A.counters = h->d_counters;
+  A.n = h->n;
+  A.npad = h->npad;
+  A.flags = h->flags;
+  A.env_offset = h->env_offset;
+  int epb = h->tpb / h->G;
+  int blocks = (h->n + epb - 1) / epb;
+  h->fn[mode]<<<blocks, h->tpb, h->smem_bytes, s>>>(A);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MMZ_OK;
+}
+
+template <int G, int NVP>
+int configure(mmz_env* h) {
+  h->G = G;
+  h->NVP = NVP;
+  // contact capacity: generous for box geoms (up to 8 points per box pair), 16 otherwise
+  int nbox = 0;
+  for (int g = 0; g < h->hm.ngeom; g++) nbox += h->hm.geom_type[g] == MMZ_GEOM_BOX;
+  int maxcon = h->hm.collision_on ? (nbox ? 24 : 16) : 1;
+  if (h->hm.ngeom <= 2 && nbox) maxcon = 16;
+  make_layout(h->hm, G, NVP, maxcon, &h->L);
+  int dev_smem = 0, sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+  const int model_smem = round_up(h->L.model_bytes, 128);
+  int best_tpb = 0, best_envs = 0, best_smem = 0;
+  for (int mode = 0; mode < 5; mode++) h->fn[mode] = mmz::get_kernel<G, NVP>(mode);
+  const int cands[] = {256, 128, 64, 32};
+  for (int tpb : cands) {
+    if (tpb < G) continue;
+    int smem = model_smem + (tpb / G) * h->L.stride * 4;
+    if (smem > dev_smem) continue;
+    for (int mode = 0; mode < 5; mode++)
+      CUDA_TRY(cudaFuncSetAttribute(h->fn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int nblk = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, h->fn[MODE_STEP], tpb, smem));
+    int envs = nblk * (tpb / G);
+    if (envs > best_envs) { best_envs = envs; best_tpb = tpb; best_smem = smem; }
+  }
+  if (!best_tpb) return fail(MMZ_ERR_CAPACITY, "workspace of %d bytes per environment does not fit in shared memory", h->L.stride * 4);
+  h->tpb = best_tpb;
+  h->smem_bytes = best_smem;
+  h->envs_per_sm = best_envs;
+  for (int mode = 0; mode < 5; mode++)
+    CUDA_TRY(cudaFuncSetAttribute(h->fn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, best_smem));
+  (void)sms;
+  return MMZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mmz_abi_version(void) { return 2; }
+const char* mmz_last_error(void) { return g_err; }
+
+int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, uint32_t flags, mmz_handle* out) {
+  if (!model_blob || !out) return fail(MMZ_ERR_INVALID, "null argument");
+  if (num_envs < 1) return fail(MMZ_ERR_INVALID, "num_envs must be >= 1");
+  if (bytes != sizeof(mmz_model)) return fail(MMZ_ERR_MODEL, "blob is %zu bytes, expected %zu", bytes, sizeof(mmz_model));
+  mmz_env* h = new (std::nothrow) mmz_env();
+  if (!h) return fail(MMZ_ERR_INVALID, "out of host memory");
+  memcpy(&h->hm, model_blob, sizeof(mmz_model));
+  int rc = validate(h->hm);
+  if (rc != MMZ_OK) { delete h; return rc; }
+  h->device = device;
+  h->n = num_envs;
+  h->npad = round_up(num_envs, 32);
+  h->flags = flags;
+  auto bail = [&](int code) { mmz_destroy(h); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(fail(MMZ_ERR_CUDA, "cudaSetDevice(%d) failed", device));
+  const int nv = h->hm.nv;
+  if (nv <= 4 && h->hm.nbody <= 8 && h->hm.ngeom <= 8) rc = configure<8, 4>(h);
+  else if (nv <= 8) rc = configure<8, 8>(h);
+  else if (nv <= 16) rc = configure<16, 16>(h);
+  else rc = configure<32, 20>(h);
+  if (rc != MMZ_OK) return bail(rc);
+  // device copy of the constants: model + derived tables, padded to a multiple of 16 bytes
+  {
+    unsigned char* host = new (std::nothrow) unsigned char[h->L.model_bytes];
+    if (!host) return bail(fail(MMZ_ERR_INVALID, "out of host memory"));
+    memset(host, 0, h->L.model_bytes);
+    memcpy(host, &h->hm, sizeof(mmz_model));
+    Derived dv;
+    make_derived(h->hm, &dv);
+    memcpy(host + round_up((int)sizeof(mmz_model), 16), &dv, sizeof dv);
+    cudaError_t e = cudaMalloc(&h->d_model, h->L.model_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_model, host, h->L.model_bytes, cudaMemcpyHostToDevice);
+    delete[] host;
+    if (e != cudaSuccess) return bail(fail(MMZ_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(e)));
+  }
+  size_t state_bytes = (size_t)h->L.nstate * h->npad * sizeof(float);
+  cudaError_t e = cudaMalloc(&h->d_state, state_bytes);
+  if (e == cudaSuccess) e = cudaMemset(h->d_state, 0, state_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_counters, 2 * (size_t)h->npad * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(h->d_counters, 0, 2 * (size_t)h->npad * sizeof(int));
+  if (e != cudaSuccess) return bail(fail(MMZ_ERR_CUDA, "state allocation failed: %s", cudaGetErrorString(e)));
+  // start every environment at qpos0 with fresh derived arrays (a model before its first reset)
+  KArgs A;
+  memset(&A, 0, sizeof A);
+  A.seed = 0;
+  {
+    mmz_model& m = h->hm;
+    float* row = new (std::nothrow) float[h->npad];
+    if (!row) return bail(fail(MMZ_ERR_INVALID, "out of host memory"));
+    for (int i = 0; i < m.nq; i++) {
+      for (int k = 0; k < h->npad; k++) row[k] = m.qpos0[i];
+      e = cudaMemcpy(h->d_state + (size_t)i * h->npad, row, h->npad * sizeof(float), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) break;
+    }
+    delete[] row;
+    if (e != cudaSuccess) return bail(fail(MMZ_ERR_CUDA, "state upload failed: %s", cudaGetErrorString(e)));
+  }
+  rc = launch(h, MODE_REFRESH, A, 0);
+  if (rc != MMZ_OK) return bail(rc);
+  if ((e = cudaStreamSynchronize(0)) != cudaSuccess)
+    return bail(fail(MMZ_ERR_CUDA, "initial refresh failed: %s", cudaGetErrorString(e)));
+  *out = h;
+  return MMZ_OK;
+}
+
+int mmz_dims(mmz_handle h, int* num_envs, int* nq, int* nv, int* nu, int* obs_dim) {
+  if (!h) return fail(MMZ_ERR_INVALID, "null handle");
+  if (num_envs) *num_envs = h->n;
+  if (nq) *nq = h->hm.nq;
+  if (nv) *nv = h->hm.nv;
+  if (nu) *nu = h->hm.nu;
+  if (obs_dim) *obs_dim = h->hm.obs_dim;
+  return MMZ_OK;
+}
+
+int mmz_kernel_config(mmz_handle h, int* lanes_per_env, int* threads_per_block, int* smem_bytes, int* envs_per_sm,
+                      int* floats_per_env) {
+  if (!h) return fail(MMZ_ERR_INVALID, "null handle");
+  if (lanes_per_env) *lanes_per_env = h->G;
+  if (threads_per_block) *threads_per_block = h->tpb;
+  if (smem_bytes) *smem_bytes = h->smem_bytes;
+  if (envs_per_sm) *envs_per_sm = h->envs_per_sm;
+  if (floats_per_env) *floats_per_env = h->L.stride;
+  return MMZ_OK;
+}
+
+int mmz_set_env_offset(mmz_handle h, int first_global_env) {
+  if (!h) return fail(MMZ_ERR_INVALID, "null handle");
+  h->env_offset = first_global_env;
+  return MMZ_OK;
+}
+
+int mmz_reset(mmz_handle h, const uint8_t* d_mask, uint64_t seed, float* d_obs, void* stream) {
+  if (!h) return fail(MMZ_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  KArgs A;
+  memset(&A, 0, sizeof A);
+  A.mask = d_mask;
+  A.seed = seed;
+  A.obs = d_obs;
+  h->seed = seed;
+  return launch(h, MODE_RESET, A, (cudaStream_t)stream);
+}
+
+int mmz_step(mmz_handle h, const float* d_action, float* d_obs, float* d_reward, uint8_t* d_done, float* d_info,
+             void* stream) {
+  if (!h) return fail(MMZ_ERR_INVALID, "null handle");
+  if (!d_action || !d_obs || !d_reward || !d_done) return fail(MMZ_ERR_INVALID, "null device pointer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  KArgs A;
+  memset(&A, 0, sizeof A);
+  A.action = d_action; A.obs = d_obs; A.reward = d_reward; A.done = d_done; A.info = d_info;
+  A.seed = h->seed;
+  return launch(h, MODE_STEP, A, (cudaStream_t)stream);
+}
+
+int mmz_step_host(mmz_handle h, const float* h_action, float* h_obs, float* h_reward, uint8_t* h_done, float* h_info,
+                  void* stream) {
+  if (!h) return fail(MMZ_ERR_INVALID, "null handle");
+  if (!h_action || !h_obs || !h_reward || !h_done) return fail(MMZ_ERR_INVALID, "null host pointer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = h->n;
+  if (!h->d_action) {
+    CUDA_TRY(cudaMalloc(&h->d_action, n * (h->hm.nu > 0 ? h->hm.nu : 1) * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->d_obs, n * h->hm.obs_dim * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->d_reward, n * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->d_info, n * 4 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->d_done, n));
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_action, h_action, n * h->hm.nu * sizeof(float), cudaMemcpyHostToDevice, s));
+  int rc = mmz_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, h_info ? h->d_info : nullptr, stream);
+  if (rc != MMZ_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs, n * h->hm.obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h_reward, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, s));
+  if (h_info) CUDA_TRY(cudaMemcpyAsync(h_info, h->d_info, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return MMZ_OK;
+}
+
+int mmz_observe(mmz_handle h, float* d_obs, void* stream) {
+  if (!h || !d_obs) return fail(MMZ_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  KArgs A;
+  memset(&A, 0, sizeof A);
+  A.obs = d_obs;
+  return launch(h, MODE_OBSERVE, A, (cudaStream_t)stream);
+}
+
+int mmz_get_state(mmz_handle h, int layout, float* d_qpos, float* d_qvel, int32_t* d_t, void* stream) {
+  if (!h) return fail(MMZ_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = h->n, npad = h->npad, nq = h->hm.nq, nv = h->hm.nv;
+  const float* rq = h->d_state;
+  const float* rv = h->d_state + (size_t)nq * npad;
+  if (layout == MMZ_LAYOUT_ENV_MAJOR) {
+    if (d_qpos) { rows_to_env_major<<<(n * nq + 255) / 256, 256, 0, s>>>(rq, d_qpos, n, npad, nq); h->launches++; }
+    if (d_qvel) { rows_to_env_major<<<(n * nv + 255) / 256, 256, 0, s>>>(rv, d_qvel, n, npad, nv); h->launches++; }
+  } else if (layout == MMZ_LAYOUT_SOA) {
+    if (d_qpos) { rows_copy<<<(n * nq + 255) / 256, 256, 0, s>>>(rq, npad, d_qpos, n, n, nq); h->launches++; }
+    if (d_qvel) { rows_copy<<<(n * nv + 255) / 256, 256, 0, s>>>(rv, npad, d_qvel, n, n, nv); h->launches++; }
+  } else {
+    return fail(MMZ_ERR_INVALID, "unknown layout %d", layout);
+  }
+  if (d_t) CUDA_TRY(cudaMemcpyAsync(d_t, h->d_counters, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaGetLastError());
+  return MMZ_OK;
+}
+
+int mmz_set_state(mmz_handle h, int layout, const float* d_qpos, const float* d_qvel, const int32_t* d_t,
+                  void* stream) {
+  if (!h) return fail(MMZ_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = h->n, npad = h->npad, nq = h->hm.nq, nv = h->hm.nv;
+  float* rq = h->d_state;
+  float* rv = h->d_state + (size_t)nq * npad;
+  if (layout == MMZ_LAYOUT_ENV_MAJOR) {
+    if (d_qpos) { env_major_to_rows<<<(n * nq + 255) / 256, 256, 0, s>>>(d_qpos, rq, n, npad, nq); h->launches++; }
+    if (d_qvel) { env_major_to_rows<<<(n * nv + 255) / 256, 256, 0, s>>>(d_qvel, rv, n, npad, nv); h->launches++; }
+  } else if (layout == MMZ_LAYOUT_SOA) {
+    if (d_qpos) { rows_copy<<<(n * nq + 255) / 256, 256, 0, s>>>(d_qpos, n, rq, npad, n, nq); h->launches++; }
+    if (d_qvel) { rows_copy<<<(n * nv + 255) / 256, 256, 0, s>>>(d_qvel, n, rv, npad, n, nv); h->launches++; }
+  } else {
+    return fail(MMZ_ERR_INVALID, "unknown layout %d", layout);
+  }
+  if (d_t) CUDA_TRY(cudaMemcpyAsync(h->d_counters, d_t, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaGetLastError());
+  KArgs A;  // MujocoEnv.set_state -> mj_forward: refresh the derived arrays
+  memset(&A, 0, sizeof A);
+  return launch(h, MODE_REFRESH, A, s);
+}
+
+int mmz_forward(mmz_handle h, const float* d_action, float* d_qacc, int32_t* d_diag, void* stream) {
+  if (!h || !d_action || !d_qacc) return fail(MMZ_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  KArgs A;
+  memset(&A, 0, sizeof A);
+  A.action = d_action; A.qacc_out = d_qacc; A.diag = d_diag;
+  return launch(h, MODE_FORWARD, A, (cudaStream_t)stream);
+}
+
+uint64_t mmz_launch_count(mmz_handle h) { return h ? h->launches : 0; }
+
+void mmz_destroy(mmz_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  cudaFree(h->d_model); cudaFree(h->d_state); cudaFree(h->d_counters);
+  cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_info); cudaFree(h->d_done);
+  delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// mmz_kernels.cuh - the fused MazeEnv.step kernel and its siblings (reset / observe / forward).
+//
+// One launch of maze_kernel<G, NVP, MODE_STEP> is one MazeEnv.step (reference
+// maze_env.py:448-481) for N lock-step environments:
+//   AgentModel.step  (point.py:44-61 teleport + 1 x mj_step | ant.py:61-73, swimmer.py:37-47
+//                     frame_skip x mj_step with RK4)          -> Env::mj_step (mmz_dyn.cuh)
+//   CollisionDetector.detect + bounce (maze_env.py:450-464, maze_env_utils.py:186-206)
+//   MazeEnv._get_obs (maze_env.py:351-369), MazeTask.reward / termination (maze_task.py:77-81
+//   and variants), TimeLimit truncation (__init__.py:31), optional in-kernel auto-reset.
+//
+// Block prologue: the model constants (mmz_model + Derived, ~8 KB) are staged into shared
+// memory by ONE 1-D bulk asynchronous copy (TMA, cp.async.bulk ... mbarrier::complete_tx) issued
+// by thread 0, while all threads load the block's tile of the structure-of-arrays state
+// (rows x EPB consecutive environments: each row segment is contiguous in HBM).
+#pragma once
+#include "mmz_dyn.cuh"
+
+namespace mmz {
+
+enum { MODE_STEP = 0, MODE_FORWARD = 1, MODE_OBSERVE = 2, MODE_RESET = 3, MODE_REFRESH = 4 };
+enum { DONE_BIT = 1, TRUNC_BIT = 2, UNSTABLE_BIT = 4 };
+enum { FLAG_AUTO_RESET = 1 };
+
+struct KArgs {
+  Layout L;
+  const void* model;   // device: mmz_model (float) + Derived, L.model_bytes
+  float* state;        // [L.nstate][npad]
+  int* counters;       // [2][npad]: t, number of resets
+  int n, npad;
+  const float* action; // [n][nu]
+  float* obs;          // [n][obs_dim]
+  float* reward;       // [n]
+  uint8_t* done;       // [n]
+  float* info;         // [n][4] or null
+  float* qacc_out;     // MODE_FORWARD: [n][nv]
+  int* diag;           // MODE_FORWARD: [n][4]
+  const uint8_t* mask; // MODE_RESET: [n] or null
+  unsigned long long seed;
+  unsigned flags;
+  int env_offset;       // global index of env 0 (keeps the Philox streams independent of the sharding)
+};
+
+MMZ_DI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// state row -> workspace offset
+MMZ_DI int row_offset(const Layout& L, int r) {
+  if (r < L.nq) return L.o_qpos + r;
+  r -= L.nq;
+  if (r < L.nv) return L.o_qvel + r;
+  r -= L.nv;
+  if (r < L.nv) return L.o_qacc + r;
+  return L.o_objpos + (r - L.nv);
+}
+
+template <int G, int NVP>
+struct Task : Env<G, NVP> {
+  using E = Env<G, NVP>;
+  using E::dv; using E::gmask; using E::lane; using E::m; using E::sync; using E::w;
+
+  // CollisionDetector.detect (maze_env_utils.py:186-206); every lane computes the same result
+  MMZ_DI bool seg_detect(const float* o, const float* n, float* point, float* refl) const {
+    float mvx = n[0] - o[0], mvy = n[1] - o[1];
+    if (sqrtf(mvx * mvx + mvy * mvy) <= 1e-8f) return false;
+    bool hit = false;
+    float bestd = 0.f;
+    for (int s = 0; s < m->nseg; s++) {
+      float x1 = m->seg[s][0], y1 = m->seg[s][1], x2 = m->seg[s][2], y2 = m->seg[s][3];
+      float wx = x2 - x1, wy = y2 - y1;
+      float sa = (wx * (o[1] - y1) - wy * (o[0] - x1)) * (wx * (n[1] - y1) - wy * (n[0] - x1));
+      float sb = (mvx * (y1 - o[1]) - mvy * (x1 - o[0])) * (mvx * (y2 - o[1]) - mvy * (x2 - o[0]));
+      if (!(sa <= 0.f && sb <= 0.f)) continue;
+      float den = wx * mvy - wy * mvx, num = wx * (y2 - o[1]) - wy * (x2 - o[0]);
+      if (den == 0.f) continue;  // collinear: the reference raises ZeroDivisionError; treated as no hit
+      float tq = num / den, px = o[0] + tq * mvx, py = o[1] + tq * mvy;
+      float d = sqrtf((px - o[0]) * (px - o[0]) + (py - o[1]) * (py - o[1]));
+      if (!hit || d < bestd) {
+        float tt = ((n[0] - x1) * wx + (n[1] - y1) * wy) / (wx * wx + wy * wy);
+        float fx = x1 + tt * wx, fy = y1 + tt * wy;
+        hit = true; bestd = d;
+        point[0] = px; point[1] = py;
+        refl[0] = fx + (fx - n[0]); refl[1] = fy + (fy - n[1]);
+      }
+    }
+    return hit;
+  }
+
+  MMZ_DI int first_goal(const float* where) const {
+    for (int g = 0; g < m->ngoal; g++) {
+      float s = 0.f;
+      for (int i = 0; i < m->goal_dim[g]; i++) { float d = where[i] - m->goal_pos[g][i]; s += d * d; }
+      if (sqrtf(s) <= m->goal_thr[g]) return g;
+    }
+    return -1;
+  }
+  MMZ_DI float goal_dist(const float* where) const {
+    float s = 0.f;
+    for (int i = 0; i < m->goal_dim[0]; i++) { float d = where[i] - m->goal_pos[0][i]; s += d * d; }
+    return sqrtf(s);
+  }
+  // MazeTask.reward / termination on the assembled observation
+  MMZ_DI void task_rules(const float* obs, float* reward, bool* term) const {
+    bool t = false;
+    if (m->term_rule == MMZ_TERM_AGENT) t = first_goal(obs) >= 0;
+    else if (m->term_rule == MMZ_TERM_OBJECT) t = first_goal(obs + 3) >= 0;
+    float r = 0.f;
+    int g;
+    switch (m->reward_rule) {
+      case MMZ_REWARD_REACH: r = t ? 1.f : m->penalty; break;
+      case MMZ_REWARD_SCALED: g = first_goal(obs); r = g >= 0 ? m->goal_scale[g] : m->penalty; break;
+      case MMZ_REWARD_SCALED_OBJECT: g = first_goal(obs + 3); r = g >= 0 ? m->goal_scale[g] : m->penalty; break;
+      case MMZ_REWARD_DIST_OBJECT: r = -goal_dist(obs + 3) / m->task_scale; break;
+      case MMZ_REWARD_DIST: r = -goal_dist(obs) / m->task_scale; break;
+      default: r = 0.f;
+    }
+    *reward = r;
+    *term = t;
+  }
+
+  // observed bodies: the reference reads data.xpos, which is only as fresh as the last kinematics pass
+  MMZ_DI void latch_objpos(const Layout& L) {
+    for (int i = lane; i < 3 * L.nobj; i += G) w[L.o_objpos + i] = w[L.o_xpos + 3 * m->obj_body[i / 3] + i % 3];
+    sync();
+  }
+  // MazeEnv._get_obs (maze_env.py:351-369) written straight to global memory, env-major
+  MMZ_DI void write_obs(const Layout& L, float* obs_g, float* obs_s, int t) {
+    const int naq = m->n_agent_q, nav = m->n_agent_v, no = 3 * L.nobj;
+    for (int i = lane; i < L.obs_dim; i += G) {
+      float v;
+      if (i < 3 && i < naq) v = w[L.o_qpos + i];
+      else if (i < 3 + no) v = w[L.o_objpos + i - 3];
+      else if (i < naq + no) v = w[L.o_qpos + i - no];
+      else if (i < naq + no + nav) v = w[L.o_qvel + i - naq - no];
+      else v = t * 0.001f;
+      obs_s[i] = v;
+      if (obs_g) obs_g[i] = v;
+    }
+    sync();
+  }
+
+  // reset_model (point.py:71-81, ant.py:84-96, swimmer.py:55-68): same distributions, Philox stream
+  MMZ_DI void reset_env(const Layout& L, unsigned long long seed, int env, int nreset, bool noise) {
+    const float amp = m->reset_noise;
+    for (int i = lane; i < L.nq; i += G) {
+      float q = m->qpos0[i];
+      if (noise && i < m->n_agent_q) {
+        uint32_t c[4] = {(uint32_t)env, (uint32_t)nreset, (uint32_t)i, 0u};
+        philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        q += amp * (2.f * u01(c[0]) - 1.f);
+      }
+      w[L.o_qpos + i] = q;
+    }
+    for (int d = lane; d < L.nv; d += G) {
+      float v = 0.f;
+      if (noise && d < m->n_agent_v) {
+        uint32_t c[4] = {(uint32_t)env, (uint32_t)nreset, (uint32_t)(64 + d), 0u};
+        philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        float u = u01(c[0]);
+        if (m->reset_kind == MMZ_RESET_POINT) v = amp * u;
+        else if (m->reset_kind == MMZ_RESET_SWIMMER) v = amp * (2.f * u - 1.f);
+        else v = amp * sqrtf(-2.f * logf(1.f - u)) * cospif(2.f * u01(c[1]));  // Box-Muller
+      }
+      w[L.o_qvel + d] = v;
+      w[L.o_qacc + d] = 0.f;
+    }
+    sync();
+    E::kinematics(L);
+    latch_objpos(L);
+  }
+
+  // MazeEnv.step for this environment. Returns the done bits.
+  MMZ_DI unsigned step(const Layout& L, const float* action, float* obs_g, float* obs_s, float* reward,
+                       float* info4, int* t_io) {
+    float* qpos = w + L.o_qpos;
+    float* qvel = w + L.o_qvel;
+    bool bad = false;
+    float inner = 0.f, fwd = 0.f, cc = 0.f;
+    const int t = *t_io + 1;
+    float before[2] = {qpos[0], qpos[1]};
+    sync();
+    if (m->step_kind == MMZ_STEP_TELEPORT) {  // PointEnv.step (point.py:44-61)
+      if (lane == 0) {
+        float ori = qpos[2] + action[1];
+        if (ori < -kPi) ori += 2.f * kPi;
+        else if (kPi < ori) ori -= 2.f * kPi;
+        float s, c;
+        sincosf(ori, &s, &c);
+        qpos[2] = ori;
+        qpos[0] += c * action[0];
+        qpos[1] += s * action[0];
+      }
+      for (int d = lane; d < L.nv; d += G) qvel[d] = fminf(fmaxf(qvel[d], -m->vel_limit), m->vel_limit);
+      for (int a = lane; a < L.nu; a += G) w[L.o_ctrl + a] = 0.f;  // the motors are never driven (point.py:56-59)
+      sync();
+      for (int k = 0; k < m->frame_skip && !bad; k++) bad = E::mj_step(L);
+      if (!bad && m->manual_collision) {  // maze_env.py:450-464
+        float nw[2] = {qpos[0], qpos[1]}, pt[2], rf[2];
+        sync();
+        if (seg_detect(before, nw, pt, rf)) {
+          float pos[2] = {pt[0] + m->restitution * (rf[0] - pt[0]), pt[1] + m->restitution * (rf[1] - pt[1])}, p2[2], r2[2];
+          if (seg_detect(before, pos, p2, r2)) { pos[0] = before[0]; pos[1] = before[1]; }
+          if (lane == 0) { qpos[0] = pos[0]; qpos[1] = pos[1]; }
+          sync();
+          E::kinematics(L);  // set_xy -> set_state -> mj_forward refreshes xpos
+        }
+      }
+    } else {  // AntEnv.step / SwimmerEnv.step (ant.py:61-73, swimmer.py:37-47)
+      for (int a = lane; a < L.nu; a += G) w[L.o_ctrl + a] = action[a];
+      sync();
+      for (int k = 0; k < m->frame_skip && !bad; k++) bad = E::mj_step(L);
+      float dt = m->timestep * m->frame_skip;
+      float vx = (qpos[0] - before[0]) / dt, vy = (qpos[1] - before[1]) / dt;
+      fwd = sqrtf(vx * vx + vy * vy);
+      for (int a = 0; a < L.nu; a++) cc += action[a] * action[a];
+      cc *= m->ctrl_cost_weight;
+      inner = m->forward_reward_weight * fwd - cc;
+    }
+    unsigned bits = 0;
+    if (bad) {  // MuJoCo's mj_checkPos/Vel/Acc auto-reset: back to qpos0, zero velocity
+      reset_env(L, 0ull, 0, 0, false);
+      bits |= UNSTABLE_BIT;
+      inner = fwd = cc = 0.f;
+    } else {
+      latch_objpos(L);
+    }
+    write_obs(L, obs_g, obs_s, t);
+    float outer;
+    bool term;
+    task_rules(obs_s, &outer, &term);
+    *reward = m->inner_reward_scale * inner + outer;
+    if (term) bits |= DONE_BIT;
+    if (m->max_episode_steps > 0 && t >= m->max_episode_steps) bits |= DONE_BIT | TRUNC_BIT;
+    info4[0] = qpos[0]; info4[1] = qpos[1]; info4[2] = fwd; info4[3] = -cc;
+    *t_io = t;
+    return bits;
+  }
+};
+
+template <int G, int NVP, int MODE>
+__global__ void maze_kernel(const __grid_constant__ KArgs A) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  const Layout& L = A.L;
+  const int tid = threadIdx.x, epb = blockDim.x / G;
+  const int env0 = blockIdx.x * epb;
+  float* wsbase = reinterpret_cast<float*>(smem + ((L.model_bytes + 127) & ~127));
+
+  // ---- model constants: one bulk async copy global -> shared, completion on an mbarrier
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(L.model_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(A.model), "r"(L.model_bytes), "r"(smem_u32(&bar)) : "memory");
+  }
+  // ---- state tile: rows x epb consecutive environments (contiguous row segments)
+  if (MODE != MODE_RESET || A.mask != nullptr) {
+    for (int idx = tid; idx < L.nstate * epb; idx += blockDim.x) {
+      int r = idx / epb, e = idx - r * epb;
+      if (env0 + e < A.n) wsbase[e * L.stride + row_offset(L, r)] = A.state[(size_t)r * A.npad + env0 + e];
+    }
+  }
+  __syncthreads();  // barrier initialised + state tile visible
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+    }
+  }
+
+  Task<G, NVP> T;
+  T.m = reinterpret_cast<const mmz_model*>(smem);
+  T.dv = reinterpret_cast<const Derived*>(smem + ((sizeof(mmz_model) + 15) & ~15));
+  const int ge = tid / G;  // group (environment) inside the block
+  T.lane = tid % G;
+  T.gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid % 32) / G * G));
+  T.w = wsbase + ge * L.stride;
+  const int env = env0 + ge;
+  float* obs_s = T.w + L.o_obs;
+
+  if (env < A.n) {
+    int t = A.counters[env], nreset = A.counters[A.npad + env];
+    if (MODE == MODE_STEP) {
+      float reward, info4[4];
+      const float* act = A.action + (size_t)env * L.nu;
+      unsigned bits = T.step(L, act, (A.flags & FLAG_AUTO_RESET) ? nullptr : A.obs + (size_t)env * L.obs_dim, obs_s,
+                             &reward, info4, &t);
+      if (A.flags & FLAG_AUTO_RESET) {
+        if (bits & DONE_BIT) {  // the env that just ended starts its next episode inside this launch
+          nreset += 1;
+          t = 0;
+          T.reset_env(L, A.seed, A.env_offset + env, nreset, true);
+        }
+        T.write_obs(L, A.obs + (size_t)env * L.obs_dim, obs_s, t);
+      }
+      if (T.lane == 0) {
+        A.reward[env] = reward;
+        A.done[env] = (uint8_t)bits;
+        A.counters[env] = t;
+        A.counters[A.npad + env] = nreset;
+      }
+      if (A.info && T.lane < 4) A.info[(size_t)env * 4 + T.lane] = info4[T.lane];
+    } else if (MODE == MODE_FORWARD) {
+      for (int a = T.lane; a < L.nu; a += G)
+        T.w[L.o_ctrl + a] = T.m->step_kind == MMZ_STEP_TELEPORT ? 0.f : A.action[(size_t)env * L.nu + a];
+      T.sync();
+      T.forward(L, false);
+      for (int d = T.lane; d < L.nv; d += G) A.qacc_out[(size_t)env * L.nv + d] = T.w[L.o_qacc + d];
+      if (A.diag && T.lane == 0) {
+        int* cn = T.cnt(L);
+        A.diag[env * 4 + 0] = cn[N_CON];
+        A.diag[env * 4 + 1] = cn[N_LIM] + 4 * cn[N_CON];
+        A.diag[env * 4 + 2] = cn[N_ITER];
+        A.diag[env * 4 + 3] = cn[N_OVERFLOW];
+      }
+    } else if (MODE == MODE_OBSERVE) {
+      T.write_obs(L, A.obs + (size_t)env * L.obs_dim, obs_s, t);
+    } else if (MODE == MODE_RESET) {
+      if (A.mask == nullptr || A.mask[env]) {
+        nreset += 1;
+        t = 0;
+        T.reset_env(L, A.seed, A.env_offset + env, nreset, true);
+        if (T.lane == 0) { A.counters[env] = 0; A.counters[A.npad + env] = nreset; }
+        if (A.obs) T.write_obs(L, A.obs + (size_t)env * L.obs_dim, obs_s, 0);
+      }
+    } else if (MODE == MODE_REFRESH) {  // after set_state: mj_forward refreshes the derived arrays
+      for (int d = T.lane; d < L.nv; d += G) T.w[L.o_qacc + d] = 0.f;
+      T.sync();
+      T.kinematics(L);
+      T.latch_objpos(L);
+    }
+  }
+  __syncthreads();
+  if (MODE == MODE_STEP || MODE == MODE_RESET || MODE == MODE_REFRESH) {
+    for (int idx = tid; idx < L.nstate * epb; idx += blockDim.x) {
+      int r = idx / epb, e = idx - r * epb;
+      if (env0 + e < A.n) A.state[(size_t)r * A.npad + env0 + e] = wsbase[e * L.stride + row_offset(L, r)];
+    }
+  }
+}
+
+typedef void (*kernel_fn)(const KArgs);
+// one translation unit per (G, NVP) instance (mmz_inst.cu, compiled in parallel)
+template <int G, int NVP>
+kernel_fn get_kernel(int mode);
+template <> kernel_fn get_kernel<8, 4>(int mode);
+template <> kernel_fn get_kernel<8, 8>(int mode);
+template <> kernel_fn get_kernel<16, 16>(int mode);
+template <> kernel_fn get_kernel<32, 20>(int mode);
+
+#ifdef MMZ_API_TU
+// [n][k] env-major <-> [k][npad] rows (get_state / set_state)
+__global__ void rows_to_env_major(const float* rows, float* out, int n, int npad, int k) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * k) { int e = i / k, r = i - e * k; out[i] = rows[(size_t)r * npad + e]; }
+}
+__global__ void env_major_to_rows(const float* in, float* rows, int n, int npad, int k) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * k) { int e = i / k, r = i - e * k; rows[(size_t)r * npad + e] = in[i]; }
+}
+__global__ void rows_copy(const float* in, int in_ld, float* out, int out_ld, int n, int k) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * k) { int r = i / n, e = i - r * n; out[(size_t)r * out_ld + e] = in[(size_t)r * in_ld + e]; }
+}
+
+#endif  // MMZ_API_TU
+
+}  // namespace mmz

@@ -1,0 +1,248 @@
+// mmz_narrow.cuh - narrow-phase contact generation (device, fp32, one thread per geom pair).
+//
+// Replaces the narrow phase of MuJoCo's mj_collision [third party; reached by the reference
+// through mj_step, call sites ant.py:63, point.py:59] for the geom types the reference's
+// assets use: plane / sphere / capsule / box (assets/point.xml:21-22, ant.xml:22-66, the
+// maze boxes of maze_env.py:138-152 and movable blocks :563-660).
+// Convention: the normal points from geom1 to geom2, dist < 0 when penetrating, the contact
+// position is midway between the two surfaces.
+#pragma once
+#include "mmz_math.cuh"
+
+namespace mmz {
+
+struct RawContact {
+  float dist, pos[3], normal[3], hint[3];
+};
+
+// sphere (centre c, radius r) against a box (centre bc, rotation bR row-major, half extents h)
+MMZ_DI int sphere_box(const float* c, float r, const float* bc, const float* bR, const float* h, float margin,
+                      RawContact* out) {
+  float rel[3] = {c[0] - bc[0], c[1] - bc[1], c[2] - bc[2]}, loc[3], dl[3];
+  matT_vec(loc, bR, rel);
+  bool inside = true;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float cl = fminf(fmaxf(loc[k], -h[k]), h[k]);
+    if (cl != loc[k]) inside = false;
+    dl[k] = cl - loc[k];
+  }
+  float nl[3] = {0.f, 0.f, 0.f}, pl[3], dist;
+  if (inside) {  // centre inside the box: leave through the nearest face
+    float best = 2.f * (h[0] + h[1] + h[2]);
+    int bi = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      float cd = fabsf(((i & 1) ? 1.f : -1.f) * h[i >> 1] - loc[i >> 1]);
+      if (cd < best) { best = cd; bi = i; }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) nl[k] = (k == (bi >> 1)) ? ((bi & 1) ? -1.f : 1.f) : 0.f;
+    dist = -best - r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) pl[k] = loc[k] + nl[k] * (r - best) * 0.5f;
+  } else {
+    float d = norm3(dl);
+    if (d - r > margin) return 0;
+    float inv = 1.f / d;
+#pragma unroll
+    for (int k = 0; k < 3; k++) nl[k] = dl[k] * inv;
+    dist = d - r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) pl[k] = loc[k] + nl[k] * (r + dist * 0.5f);
+  }
+  if (dist > margin) return 0;
+  out->dist = dist;
+  mat_vec(out->normal, bR, nl);
+  mat_vec(out->pos, bR, pl);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { out->pos[k] += bc[k]; out->hint[k] = 0.f; }
+  return 1;
+}
+
+MMZ_DI float box_excess_deriv(const float* a, const float* b, float t, const float* h) {
+  float g = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float x = a[k] + b[k] * t;
+    float ex = x > h[k] ? x - h[k] : (x < -h[k] ? x + h[k] : 0.f);
+    g += ex * b[k];
+  }
+  return g;
+}
+
+// capsule (segment p0-p1, radius r) against a box: both end caps when both are within the margin,
+// otherwise one contact at the segment point nearest the box (root of the monotone
+// piecewise-linear derivative of the squared distance along the segment).
+MMZ_DI int capsule_box(const float* p0, const float* p1, float r, const float* bc, const float* bR, const float* h,
+                       float margin, RawContact* out) {
+  RawContact c0, c1;
+  int n0 = sphere_box(p0, r, bc, bR, h, margin, &c0);
+  int n1 = sphere_box(p1, r, bc, bR, h, margin, &c1);
+  if (n0 && n1) { out[0] = c0; out[1] = c1; return 2; }
+  float a[3], b[3], rel[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) rel[k] = p0[k] - bc[k];
+  matT_vec(a, bR, rel);
+#pragma unroll
+  for (int k = 0; k < 3; k++) rel[k] = p1[k] - p0[k];
+  matT_vec(b, bR, rel);
+  float glo = box_excess_deriv(a, b, 0.f, h), ghi = box_excess_deriv(a, b, 1.f, h), ts;
+  if (glo > 0.f) ts = 0.f;
+  else if (ghi <= 0.f) ts = 1.f;
+  else {
+    float tlo = 0.f, thi = 1.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (fabsf(b[k]) > kMinVal) {
+#pragma unroll
+        for (int s = -1; s <= 1; s += 2) {
+          float t = (s * h[k] - a[k]) / b[k];
+          if (t > 0.f && t < 1.f) {
+            float g = box_excess_deriv(a, b, t, h);
+            if (g <= 0.f) { if (t > tlo) { tlo = t; glo = g; } }
+            else if (t < thi) { thi = t; ghi = g; }
+          }
+        }
+      }
+    }
+    ts = (ghi - glo) > kMinVal ? tlo + (-glo) * (thi - tlo) / (ghi - glo) : tlo;
+  }
+  float ps[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) ps[k] = p0[k] + ts * (p1[k] - p0[k]);
+  return sphere_box(ps, r, bc, bR, h, margin, out);
+}
+
+// box against box: separating-axis search, then face clipping or an edge-edge point.
+// Normal from box A to box B; up to 8 contacts. Runs on a single lane (rare geoms: Point's
+// arrow box point.xml:22 and movable blocks), so it favours clarity over register use.
+static __device__ __noinline__ int box_box(const float* ca, const float* Ra, const float* ha, const float* cb,
+                                    const float* Rb, const float* hb, float margin, RawContact* out) {
+  float A[3][3], B[3][3], d[3];
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) { A[i][k] = Ra[3 * k + i]; B[i][k] = Rb[3 * k + i]; }
+  for (int k = 0; k < 3; k++) d[k] = cb[k] - ca[k];
+  float best_f = -3.0e38f, best_e = -3.0e38f, nf[3] = {0, 0, 0}, ne[3] = {0, 0, 0};
+  int code_f = -1, code_e = -1;
+  for (int code = 0; code < 15; code++) {
+    float L[3];
+    if (code < 3) { L[0] = A[code][0]; L[1] = A[code][1]; L[2] = A[code][2]; }
+    else if (code < 6) { L[0] = B[code - 3][0]; L[1] = B[code - 3][1]; L[2] = B[code - 3][2]; }
+    else {
+      cross3(L, A[(code - 6) / 3], B[(code - 6) % 3]);
+      float n = norm3(L);
+      if (n < 1e-6f) continue;  // parallel edges: covered by the face axes
+      float inv = 1.f / n;
+      L[0] *= inv; L[1] *= inv; L[2] *= inv;
+    }
+    float ra = 0.f, rb = 0.f;
+    for (int i = 0; i < 3; i++) { ra += ha[i] * fabsf(dot3(L, A[i])); rb += hb[i] * fabsf(dot3(L, B[i])); }
+    float dl = dot3(L, d);
+    float s = fabsf(dl) - ra - rb;
+    if (s > margin) return 0;
+    float sg = dl < 0.f ? -1.f : 1.f;
+    if (code < 6) {
+      if (s > best_f) { best_f = s; code_f = code; nf[0] = sg * L[0]; nf[1] = sg * L[1]; nf[2] = sg * L[2]; }
+    } else if (s > best_e) { best_e = s; code_e = code; ne[0] = sg * L[0]; ne[1] = sg * L[1]; ne[2] = sg * L[2]; }
+  }
+  float best, bn[3];
+  int bcode;
+  if (code_e >= 0 && best_e > best_f + 1e-6f + 0.05f * fabsf(best_f)) { best = best_e; bcode = code_e; bn[0] = ne[0]; bn[1] = ne[1]; bn[2] = ne[2]; }
+  else { best = best_f; bcode = code_f; bn[0] = nf[0]; bn[1] = nf[1]; bn[2] = nf[2]; }
+  if (bcode < 0) return 0;
+  if (bcode >= 6) {  // edge-edge
+    int ia = (bcode - 6) / 3, ib = (bcode - 6) % 3;
+    float pa[3] = {ca[0], ca[1], ca[2]}, pb[3] = {cb[0], cb[1], cb[2]};
+    for (int i = 0; i < 3; i++) {
+      if (i != ia) { float sg = dot3(bn, A[i]) > 0.f ? 1.f : -1.f; for (int k = 0; k < 3; k++) pa[k] += sg * ha[i] * A[i][k]; }
+      if (i != ib) { float sg = dot3(bn, B[i]) > 0.f ? -1.f : 1.f; for (int k = 0; k < 3; k++) pb[k] += sg * hb[i] * B[i][k]; }
+    }
+    float w[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]}, ua = 0.f, ub = 0.f;
+    float uaub = dot3(A[ia], B[ib]), q1 = dot3(A[ia], w), q2 = -dot3(B[ib], w), den = 1.f - uaub * uaub;
+    if (den > 1e-9f) { ua = (q1 + uaub * q2) / den; ub = (uaub * q1 + q2) / den; }
+    ua = fminf(fmaxf(ua, -ha[ia]), ha[ia]);
+    ub = fminf(fmaxf(ub, -hb[ib]), hb[ib]);
+    for (int k = 0; k < 3; k++) {
+      float xa = pa[k] + ua * A[ia][k], xb = pb[k] + ub * B[ib][k];
+      out->pos[k] = 0.5f * (xa + xb);
+      out->normal[k] = bn[k];
+      out->hint[k] = 0.f;
+    }
+    out->dist = best;
+    return 1;
+  }
+  // face contact: the reference box owns the axis, the incident box is the other
+  const float *cr, *hr, *ci, *hi;
+  float(*Rr)[3], (*Ri)[3];
+  float nr[3];
+  int ax;
+  if (bcode < 3) { cr = ca; hr = ha; Rr = A; ci = cb; hi = hb; Ri = B; ax = bcode; nr[0] = bn[0]; nr[1] = bn[1]; nr[2] = bn[2]; }
+  else { cr = cb; hr = hb; Rr = B; ci = ca; hi = ha; Ri = A; ax = bcode - 3; nr[0] = -bn[0]; nr[1] = -bn[1]; nr[2] = -bn[2]; }
+  int iax = 0;
+  float mind = 3.0e38f;
+  for (int i = 0; i < 3; i++) {
+    float v = fabsf(dot3(nr, Ri[i]));
+    if (-v < mind) { mind = -v; iax = i; }
+  }
+  float isg = dot3(nr, Ri[iax]) > 0.f ? -1.f : 1.f;
+  int u = (iax + 1) % 3, v = (iax + 2) % 3;
+  float poly[16][3], tmp[16][3];
+  int np = 4;
+  for (int c = 0; c < 4; c++) {
+    float su = (c == 0 || c == 3) ? -1.f : 1.f, sv = (c < 2) ? -1.f : 1.f;
+    for (int k = 0; k < 3; k++)
+      poly[c][k] = ci[k] + isg * hi[iax] * Ri[iax][k] + su * hi[u] * Ri[u][k] + sv * hi[v] * Ri[v][k];
+  }
+  int ru = (ax + 1) % 3, rv = (ax + 2) % 3;
+  for (int side = 0; side < 4; side++) {
+    const float* axs = Rr[side < 2 ? ru : rv];
+    float sg = (side & 1) ? -1.f : 1.f, lim = hr[side < 2 ? ru : rv];
+    int nn = 0;
+    for (int i = 0; i < np; i++) {
+      const float *p = poly[i], *q = poly[(i + 1) % np];
+      float rp[3] = {p[0] - cr[0], p[1] - cr[1], p[2] - cr[2]}, rq[3] = {q[0] - cr[0], q[1] - cr[1], q[2] - cr[2]};
+      float dp = sg * dot3(axs, rp) - lim, dq = sg * dot3(axs, rq) - lim;
+      if (dp <= 0.f) { tmp[nn][0] = p[0]; tmp[nn][1] = p[1]; tmp[nn][2] = p[2]; nn++; }
+      if ((dp <= 0.f) != (dq <= 0.f)) {
+        float t = dp / (dp - dq);
+        for (int k = 0; k < 3; k++) tmp[nn][k] = p[k] + t * (q[k] - p[k]);
+        nn++;
+      }
+    }
+    np = nn;
+    for (int i = 0; i < np; i++) { poly[i][0] = tmp[i][0]; poly[i][1] = tmp[i][1]; poly[i][2] = tmp[i][2]; }
+    if (np == 0) return 0;
+  }
+  int n = 0;
+  for (int i = 0; i < np && n < 8; i++) {
+    float rp[3] = {poly[i][0] - cr[0], poly[i][1] - cr[1], poly[i][2] - cr[2]};
+    float depth = dot3(nr, rp) - hr[ax];
+    if (depth >= margin) continue;
+    for (int k = 0; k < 3; k++) {
+      out[n].pos[k] = poly[i][k] - nr[k] * depth * 0.5f;
+      out[n].normal[k] = bn[k];
+      out[n].hint[k] = 0.f;
+    }
+    out[n].dist = depth;
+    n++;
+  }
+  return n;
+}
+
+// orthonormal contact frame from a normal and an optional tangent hint (rows: n, t1, t2)
+MMZ_DI void make_frame(float* fr) {
+  float inv = 1.f / norm3(fr);
+  fr[0] *= inv; fr[1] *= inv; fr[2] *= inv;
+  if (norm3(fr + 3) < 0.5f) {
+    fr[3] = fr[4] = fr[5] = 0.f;
+    if (fr[1] < 0.5f && fr[1] > -0.5f) fr[4] = 1.f; else fr[5] = 1.f;
+  }
+  float d = dot3(fr, fr + 3);
+  fr[3] -= d * fr[0]; fr[4] -= d * fr[1]; fr[5] -= d * fr[2];
+  inv = 1.f / norm3(fr + 3);
+  fr[3] *= inv; fr[4] *= inv; fr[5] *= inv;
+  cross3(fr + 6, fr, fr + 3);
+}
+
+}  // namespace mmz

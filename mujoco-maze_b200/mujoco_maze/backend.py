@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_PKG_ROOT, "libmmz.so")
 MMZ_DONE, MMZ_TRUNCATED, MMZ_UNSTABLE = 1, 2, 4
 MMZ_AUTO_RESET = 1
 LAYOUT_ENV_MAJOR, LAYOUT_SOA = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 
@@ -45,6 +45,8 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     sig = {
         "mmz_create": ([vp, sz, i32, i32, u32, ctypes.POINTER(vp)], i32),
         "mmz_dims": ([vp, ip, ip, ip, ip, ip], i32),
+        "mmz_kernel_config": ([vp, ip, ip, ip, ip, ip], i32),
+        "mmz_set_env_offset": ([vp, i32], i32),
         "mmz_reset": ([vp, vp, u64, vp, vp], i32),
         "mmz_step": ([vp, vp, vp, vp, vp, vp, vp], i32),
         "mmz_step_host": ([vp, vp, vp, vp, vp, vp, vp], i32),
@@ -68,7 +70,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = (
-    "mmz_create", "mmz_dims", "mmz_reset", "mmz_step", "mmz_step_host", "mmz_observe", "mmz_get_state",
+    "mmz_create", "mmz_dims", "mmz_kernel_config", "mmz_set_env_offset", "mmz_reset", "mmz_step", "mmz_step_host", "mmz_observe", "mmz_get_state",
     "mmz_set_state", "mmz_forward", "mmz_launch_count", "mmz_last_error", "mmz_destroy", "mmz_abi_version",
 )
 
@@ -80,7 +82,7 @@ def _ptr(t) -> Optional[int]:
 class BatchedSim:
     """N lock-step environments on one CUDA device (one `mmz_handle`)."""
 
-    def __init__(self, model, num_envs: int, device="cuda:0", auto_reset: bool = False):
+    def __init__(self, model, num_envs: int, device="cuda:0", auto_reset: bool = False, env_offset: int = 0):
         import torch
 
         self.torch = torch
@@ -100,6 +102,13 @@ class BatchedSim:
         dims = [ctypes.c_int() for _ in range(5)]
         self._check(self.lib.mmz_dims(self._h, *[ctypes.byref(d) for d in dims]))
         _, self.nq, self.nv, self.nu, self.obs_dim = (d.value for d in dims)
+        cfg = [ctypes.c_int() for _ in range(5)]
+        self._check(self.lib.mmz_kernel_config(self._h, *[ctypes.byref(c) for c in cfg]))
+        self.kernel_config = dict(zip(
+            ("lanes_per_env", "threads_per_block", "smem_bytes", "envs_per_sm", "floats_per_env"),
+            (c.value for c in cfg)))
+        if env_offset:
+            self._check(self.lib.mmz_set_env_offset(self._h, int(env_offset)))
         dev = self.device
         self.obs = torch.empty((self.n, self.obs_dim), dtype=torch.float32, device=dev)
         self.reward = torch.empty((self.n,), dtype=torch.float32, device=dev)

@@ -1269,3 +1269,47 @@ long ora_rollout(const void* blob, size_t bytes, int n, const double* qpos, cons
   }
   return total;
 }
+
+/* Persistent batch of independent environments (CPU baseline legs of bench.py, tests):
+ * state survives between calls, one OpenMP thread per chunk of environments. */
+typedef struct ora_batch {
+  int n;
+  ora_env** env;
+} ora_batch;
+
+ora_batch* ora_batch_create(const void* blob, size_t bytes, int n) {
+  ora_batch* b = (ora_batch*)calloc(1, sizeof(ora_batch));
+  b->n = n;
+  b->env = (ora_env**)calloc((size_t)n, sizeof(ora_env*));
+  for (int i = 0; i < n; i++) {
+    b->env[i] = ora_create(blob, bytes);
+    if (!b->env[i]) { for (int k = 0; k < i; k++) ora_destroy(b->env[k]); free(b->env); free(b); return NULL; }
+    b->env[i]->use_warmstart = 1;
+  }
+  return b;
+}
+void ora_batch_destroy(ora_batch* b) {
+  if (!b) return;
+  for (int i = 0; i < b->n; i++) ora_destroy(b->env[i]);
+  free(b->env);
+  free(b);
+}
+/* qpos [n][nq], qvel [n][nv] */
+void ora_batch_set_state(ora_batch* b, const double* qpos, const double* qvel) {
+  for (int i = 0; i < b->n; i++)
+    ora_set_state(b->env[i], qpos + (size_t)i * b->env[i]->m.nq, qvel + (size_t)i * b->env[i]->m.nv, 0);
+}
+/* one MazeEnv.step for every environment: actions [n][nu] -> obs [n][obs_dim], reward [n], done bits [n] */
+long ora_batch_step(ora_batch* b, const double* actions, double* obs, double* reward, int* done, int nthreads) {
+  const int n = b->n;
+  if (n == 0) return 0;
+  const int nu = b->env[0]->m.nu, od = b->env[0]->m.obs_dim;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 4)
+#endif
+  for (int i = 0; i < n; i++) {
+    double info[4];
+    done[i] = ora_step(b->env[i], actions + (size_t)i * nu, obs + (size_t)i * od, reward + i, info);
+  }
+  return n;
+}

@@ -55,6 +55,10 @@ def lib() -> ctypes.CDLL:
         L.ora_rollout.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, dp, dp, dp, ctypes.c_int,
                                   ctypes.c_int, dp, dp]
         L.ora_rollout.restype = ctypes.c_long
+        L.ora_batch_create.argtypes, L.ora_batch_create.restype = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int], vp
+        L.ora_batch_destroy.argtypes = [vp]
+        L.ora_batch_set_state.argtypes = [vp, dp, dp]
+        L.ora_batch_step.argtypes, L.ora_batch_step.restype = [vp, dp, dp, dp, ip, ctypes.c_int], ctypes.c_long
         _lib = L
     return _lib
 
@@ -181,3 +185,39 @@ def rollout(model, qpos, qvel, actions, nthreads=1):
     obs, rew = np.zeros((n, int(model.obs_dim))), np.zeros(n)
     done = L.ora_rollout(blob, len(blob), n, _d(qpos), _d(qvel), _d(actions), steps, int(nthreads), _d(obs), _d(rew))
     return done, obs, rew
+
+
+class OracleBatch:
+    """n persistent environments of the fp64 restatement stepped by OpenMP threads (CPU baseline)."""
+
+    def __init__(self, model, n):
+        self.L = lib()
+        blob = model.blob(8)
+        self.n, self.nq, self.nv, self.nu = int(n), int(model.nq), int(model.nv), int(model.nu)
+        self.obs_dim = int(model.obs_dim)
+        self.h = self.L.ora_batch_create(blob, len(blob), self.n)
+        if not self.h:
+            raise RuntimeError("ora_batch_create rejected the model blob")
+        self.obs = np.zeros((self.n, self.obs_dim))
+        self.reward = np.zeros(self.n)
+        self.done = np.zeros(self.n, dtype=np.int32)
+
+    def set_state(self, qpos, qvel):
+        self.L.ora_batch_set_state(self.h, _d(_arr(qpos, self.n * self.nq)), _d(_arr(qvel, self.n * self.nv)))
+
+    def step(self, actions, nthreads=1):
+        a = _arr(actions, self.n * self.nu)
+        self.L.ora_batch_step(self.h, _d(a), _d(self.obs), _d(self.reward),
+                              self.done.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), int(nthreads))
+        return self.obs, self.reward, self.done
+
+    def close(self):
+        if self.h:
+            self.L.ora_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
