@@ -63,7 +63,7 @@ def make_model(env_id):
     import mujoco_maze  # noqa: F401
     from mujoco_maze import gym
 
-    return gym.make(env_id).unwrapped.model
+    return gym.make(env_id, num_envs=1).unwrapped.model  # batched flavour: TimeLimit (1000) inside the kernel
 
 
 def initial_state(model, n, seed):

@@ -113,6 +113,11 @@ int mmz_set_state(mmz_handle h, int layout, const float* d_qpos, const float* d_
  * Test / debugging aid for parity against the oracle. */
 int mmz_forward(mmz_handle h, const float* d_action, float* d_qacc, int32_t* d_diag, void* stream);
 
+/* Optional solver diagnostics of mmz_step: when d_diag is non-NULL every following step writes
+ * diag [N][4] = {Newton iterations, line-search iterations, max simultaneous contacts, solves
+ * that hit the iteration cap}, summed over the forward evaluations of that step. NULL disables. */
+int mmz_set_step_diag(mmz_handle h, int32_t* d_diag);
+
 /* Number of CUDA kernels this handle has launched so far. */
 uint64_t mmz_launch_count(mmz_handle h);
 

@@ -56,6 +56,7 @@ struct mmz_env {
   uint8_t* d_done = nullptr;
   unsigned long long seed = 0;
   unsigned long long launches = 0;
+  int32_t* d_step_diag = nullptr;  // caller-owned, optional
   kernel_fn fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -116,6 +117,7 @@ void make_derived(const mmz_model& m, Derived* d) {
     if (m.body_level[b] + 1 > nlev) nlev = m.body_level[b] + 1;
   }
   d->nlev = nlev;
+  d->ident[0] = d->ident[4] = d->ident[8] = 1.f;
   for (int g = 0; g < m.ngeom; g++)
     if (m.geom_type[g] == MMZ_GEOM_BOX) d->boxg[d->nboxg++] = g;
 }
@@ -197,7 +199,7 @@ int configure(mmz_env* h) {
 
 extern "C" {
 
-int mmz_abi_version(void) { return 2; }
+int mmz_abi_version(void) { return 3; }
 const char* mmz_last_error(void) { return g_err; }
 
 int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, uint32_t flags, mmz_handle* out) {
@@ -286,6 +288,12 @@ int mmz_kernel_config(mmz_handle h, int* lanes_per_env, int* threads_per_block, 
   return MMZ_OK;
 }
 
+int mmz_set_step_diag(mmz_handle h, int32_t* d_diag) {
+  if (!h) return fail(MMZ_ERR_INVALID, "null handle");
+  h->d_step_diag = d_diag;
+  return MMZ_OK;
+}
+
 int mmz_set_env_offset(mmz_handle h, int first_global_env) {
   if (!h) return fail(MMZ_ERR_INVALID, "null handle");
   h->env_offset = first_global_env;
@@ -313,6 +321,7 @@ int mmz_step(mmz_handle h, const float* d_action, float* d_obs, float* d_reward,
   memset(&A, 0, sizeof A);
   A.action = d_action; A.obs = d_obs; A.reward = d_reward; A.done = d_done; A.info = d_info;
   A.seed = h->seed;
+  A.diag = h->d_step_diag;
   return launch(h, MODE_STEP, A, (cudaStream_t)stream);
 }
 

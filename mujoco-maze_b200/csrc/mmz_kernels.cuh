@@ -33,7 +33,8 @@ struct KArgs {
   uint8_t* done;       // [n]
   float* info;         // [n][4] or null
   float* qacc_out;     // MODE_FORWARD: [n][nv]
-  int* diag;           // MODE_FORWARD: [n][4]
+  int* diag;           // MODE_FORWARD: [n][4] {contacts, rows, iterations, overflow}; MODE_STEP (optional):
+                       // [n][4] {Newton iterations, line-search iterations, max contacts, capped solves} of the step
   const uint8_t* mask; // MODE_RESET: [n] or null
   unsigned long long seed;
   unsigned flags;
@@ -137,101 +138,137 @@ struct Task : Env<G, NVP> {
     sync();
   }
 
-  // reset_model (point.py:71-81, ant.py:84-96, swimmer.py:55-68): same distributions, Philox stream
-  MMZ_DI void reset_env(const Layout& L, unsigned long long seed, int env, int nreset, bool noise) {
+  // reset_model (point.py:71-81, ant.py:84-96, swimmer.py:55-68): same distributions, Philox stream.
+  // Only writes qpos / qvel / qacc; the caller refreshes the derived arrays (finish()).
+  MMZ_DI void reset_state(const Layout& L, unsigned long long seed, int env, int nreset, bool noise) {
     const float amp = m->reset_noise;
-    for (int i = lane; i < L.nq; i += G) {
-      float q = m->qpos0[i];
-      if (noise && i < m->n_agent_q) {
-        uint32_t c[4] = {(uint32_t)env, (uint32_t)nreset, (uint32_t)i, 0u};
-        philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-        q += amp * (2.f * u01(c[0]) - 1.f);
-      }
-      w[L.o_qpos + i] = q;
-    }
-    for (int d = lane; d < L.nv; d += G) {
-      float v = 0.f;
-      if (noise && d < m->n_agent_v) {
-        uint32_t c[4] = {(uint32_t)env, (uint32_t)nreset, (uint32_t)(64 + d), 0u};
+#pragma unroll 1
+    for (int i = lane; i < L.nq + L.nv; i += G) {
+      const bool isq = i < L.nq;
+      const int k = isq ? i : i - L.nq;
+      float val = isq ? m->qpos0[k] : 0.f;
+      if (noise && k < (isq ? m->n_agent_q : m->n_agent_v)) {
+        uint32_t c[4] = {(uint32_t)env, (uint32_t)nreset, (uint32_t)(isq ? k : 64 + k), 0u};
         philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
         float u = u01(c[0]);
-        if (m->reset_kind == MMZ_RESET_POINT) v = amp * u;
-        else if (m->reset_kind == MMZ_RESET_SWIMMER) v = amp * (2.f * u - 1.f);
-        else v = amp * sqrtf(-2.f * logf(1.f - u)) * cospif(2.f * u01(c[1]));  // Box-Muller
+        if (isq || m->reset_kind == MMZ_RESET_SWIMMER) val += amp * (2.f * u - 1.f);
+        else if (m->reset_kind == MMZ_RESET_POINT) val += amp * u;
+        else val += amp * sqrtf(-2.f * logf(1.f - u)) * cospif(2.f * u01(c[1]));  // Box-Muller
       }
-      w[L.o_qvel + d] = v;
-      w[L.o_qacc + d] = 0.f;
+      if (isq) w[L.o_qpos + k] = val;
+      else { w[L.o_qvel + k] = val; w[L.o_qacc + k] = 0.f; }
     }
     sync();
-    E::kinematics(L);
-    latch_objpos(L);
   }
 
-  // MazeEnv.step for this environment. Returns the done bits.
-  MMZ_DI unsigned step(const Layout& L, const float* action, float* obs_g, float* obs_s, float* reward,
-                       float* info4, int* t_io) {
+  // MazeEnv.step for this environment (maze_env.py:448-481). Returns the done bits.
+  // Tail passes (one kinematics / observation call site): pass 0 closes the step itself (clamp or
+  // blow-up refresh, obs, reward, done); pass 1 runs only when the episode ended and auto-reset is
+  // on, and re-observes the fresh episode.
+  MMZ_DI unsigned step(const Layout& L, const float* action, float* obs_g, float* obs_s, float* reward, float* info4,
+                       int* t_io, int* nreset_io, bool auto_reset, unsigned long long seed, int genv) {
     float* qpos = w + L.o_qpos;
     float* qvel = w + L.o_qvel;
+    const bool teleport = m->step_kind == MMZ_STEP_TELEPORT;
     bool bad = false;
     float inner = 0.f, fwd = 0.f, cc = 0.f;
-    const int t = *t_io + 1;
-    float before[2] = {qpos[0], qpos[1]};
+    int t = *t_io + 1;
+    const float before[2] = {qpos[0], qpos[1]};
     sync();
-    if (m->step_kind == MMZ_STEP_TELEPORT) {  // PointEnv.step (point.py:44-61)
+    if (teleport) {  // PointEnv.step (point.py:44-61): turn, move, clip qvel; the motors are never driven
       if (lane == 0) {
         float ori = qpos[2] + action[1];
         if (ori < -kPi) ori += 2.f * kPi;
         else if (kPi < ori) ori -= 2.f * kPi;
-        float s, c;
-        sincosf(ori, &s, &c);
+        float sn, cs;
+        sincosf(ori, &sn, &cs);
         qpos[2] = ori;
-        qpos[0] += c * action[0];
-        qpos[1] += s * action[0];
+        qpos[0] += cs * action[0];
+        qpos[1] += sn * action[0];
       }
       for (int d = lane; d < L.nv; d += G) qvel[d] = fminf(fmaxf(qvel[d], -m->vel_limit), m->vel_limit);
-      for (int a = lane; a < L.nu; a += G) w[L.o_ctrl + a] = 0.f;  // the motors are never driven (point.py:56-59)
-      sync();
-      for (int k = 0; k < m->frame_skip && !bad; k++) bad = E::mj_step(L);
-      if (!bad && m->manual_collision) {  // maze_env.py:450-464
-        float nw[2] = {qpos[0], qpos[1]}, pt[2], rf[2];
-        sync();
-        if (seg_detect(before, nw, pt, rf)) {
-          float pos[2] = {pt[0] + m->restitution * (rf[0] - pt[0]), pt[1] + m->restitution * (rf[1] - pt[1])}, p2[2], r2[2];
-          if (seg_detect(before, pos, p2, r2)) { pos[0] = before[0]; pos[1] = before[1]; }
-          if (lane == 0) { qpos[0] = pos[0]; qpos[1] = pos[1]; }
+    }
+    for (int a = lane; a < L.nu; a += G) w[L.o_ctrl + a] = teleport ? 0.f : action[a];
+    sync();
+#pragma unroll 1
+    for (int k = 0; k < m->frame_skip && !bad; k++) bad = E::mj_step(L);
+    bool refresh = bad;
+    if (!bad) {
+      if (teleport) {
+        if (m->manual_collision) {  // maze_env.py:450-464
+          float nw[2] = {qpos[0], qpos[1]}, pos[2];
           sync();
-          E::kinematics(L);  // set_xy -> set_state -> mj_forward refreshes xpos
+          if (clamp_move(before, nw, pos)) {
+            if (lane == 0) { qpos[0] = pos[0]; qpos[1] = pos[1]; }
+            refresh = true;  // set_xy -> set_state -> mj_forward refreshes xpos
+          }
         }
+      } else {  // AntEnv.step / SwimmerEnv.step (ant.py:61-73, swimmer.py:37-47)
+        float dt = m->timestep * m->frame_skip;
+        float vx = (qpos[0] - before[0]) / dt, vy = (qpos[1] - before[1]) / dt;
+        fwd = sqrtf(vx * vx + vy * vy);
+        for (int a = 0; a < L.nu; a++) cc += action[a] * action[a];
+        cc *= m->ctrl_cost_weight;
+        inner = m->forward_reward_weight * fwd - cc;
       }
-    } else {  // AntEnv.step / SwimmerEnv.step (ant.py:61-73, swimmer.py:37-47)
-      for (int a = lane; a < L.nu; a += G) w[L.o_ctrl + a] = action[a];
-      sync();
-      for (int k = 0; k < m->frame_skip && !bad; k++) bad = E::mj_step(L);
-      float dt = m->timestep * m->frame_skip;
-      float vx = (qpos[0] - before[0]) / dt, vy = (qpos[1] - before[1]) / dt;
-      fwd = sqrtf(vx * vx + vy * vy);
-      for (int a = 0; a < L.nu; a++) cc += action[a] * action[a];
-      cc *= m->ctrl_cost_weight;
-      inner = m->forward_reward_weight * fwd - cc;
     }
     unsigned bits = 0;
     if (bad) {  // MuJoCo's mj_checkPos/Vel/Acc auto-reset: back to qpos0, zero velocity
-      reset_env(L, 0ull, 0, 0, false);
       bits |= UNSTABLE_BIT;
       inner = fwd = cc = 0.f;
-    } else {
-      latch_objpos(L);
     }
-    write_obs(L, obs_g, obs_s, t);
-    float outer;
-    bool term;
-    task_rules(obs_s, &outer, &term);
-    *reward = m->inner_reward_scale * inner + outer;
-    if (term) bits |= DONE_BIT;
-    if (m->max_episode_steps > 0 && t >= m->max_episode_steps) bits |= DONE_BIT | TRUNC_BIT;
-    info4[0] = qpos[0]; info4[1] = qpos[1]; info4[2] = fwd; info4[3] = -cc;
+    bool reset_now = bad, noise = false;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      if (reset_now) reset_state(L, seed, genv, *nreset_io, noise);
+      sync();
+      if (refresh) E::kinematics(L);
+      latch_objpos(L);
+      write_obs(L, (pass == 1 || !auto_reset) ? obs_g : nullptr, obs_s, t);
+      if (pass == 0) {
+        float outer;
+        bool term;
+        task_rules(obs_s, &outer, &term);
+        *reward = m->inner_reward_scale * inner + outer;
+        if (term) bits |= DONE_BIT;
+        if (m->max_episode_steps > 0 && t >= m->max_episode_steps) bits |= DONE_BIT | TRUNC_BIT;
+        info4[0] = qpos[0]; info4[1] = qpos[1]; info4[2] = fwd; info4[3] = -cc;
+        if (!(auto_reset && (bits & DONE_BIT))) {
+          if (auto_reset) {  // no reset: the observation just assembled is the one to return
+            for (int i = lane; i < L.obs_dim; i += G) obs_g[i] = obs_s[i];
+          }
+          break;
+        }
+        // the env that just ended starts its next episode inside this launch
+        *nreset_io += 1;
+        t = 0;
+        reset_now = true; noise = true; refresh = true;
+      }
+    }
     *t_io = t;
     return bits;
+  }
+
+  // CollisionDetector.detect + the bounce of maze_env.py:457-464: true if the move old -> nw crossed
+  // a wall segment; pos = bounce position, or `old` when the bounce crosses a wall again.
+  MMZ_DI bool clamp_move(const float* old, const float* nw, float* pos) const {
+    bool hit = false;
+    float target[2] = {nw[0], nw[1]};
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      float pt[2], rf[2];
+      bool h = seg_detect(old, target, pt, rf);
+      if (pass == 0) {
+        if (!h) return false;
+        hit = true;
+        target[0] = pt[0] + m->restitution * (rf[0] - pt[0]);
+        target[1] = pt[1] + m->restitution * (rf[1] - pt[1]);
+      } else if (h) {
+        target[0] = old[0]; target[1] = old[1];
+      }
+    }
+    pos[0] = target[0]; pos[1] = target[1];
+    return hit;
   }
 };
 
@@ -284,17 +321,11 @@ __global__ void maze_kernel(const __grid_constant__ KArgs A) {
     int t = A.counters[env], nreset = A.counters[A.npad + env];
     if (MODE == MODE_STEP) {
       float reward, info4[4];
+      if (T.lane < 4) T.cnt(L)[N_ITER_SUM + T.lane] = 0;
+      T.sync();
       const float* act = A.action + (size_t)env * L.nu;
-      unsigned bits = T.step(L, act, (A.flags & FLAG_AUTO_RESET) ? nullptr : A.obs + (size_t)env * L.obs_dim, obs_s,
-                             &reward, info4, &t);
-      if (A.flags & FLAG_AUTO_RESET) {
-        if (bits & DONE_BIT) {  // the env that just ended starts its next episode inside this launch
-          nreset += 1;
-          t = 0;
-          T.reset_env(L, A.seed, A.env_offset + env, nreset, true);
-        }
-        T.write_obs(L, A.obs + (size_t)env * L.obs_dim, obs_s, t);
-      }
+      unsigned bits = T.step(L, act, A.obs + (size_t)env * L.obs_dim, obs_s, &reward, info4, &t, &nreset,
+                             (A.flags & FLAG_AUTO_RESET) != 0, A.seed, A.env_offset + env);
       if (T.lane == 0) {
         A.reward[env] = reward;
         A.done[env] = (uint8_t)bits;
@@ -302,6 +333,7 @@ __global__ void maze_kernel(const __grid_constant__ KArgs A) {
         A.counters[A.npad + env] = nreset;
       }
       if (A.info && T.lane < 4) A.info[(size_t)env * 4 + T.lane] = info4[T.lane];
+      if (A.diag && T.lane < 4) A.diag[(size_t)env * 4 + T.lane] = T.cnt(L)[N_ITER_SUM + T.lane];
     } else if (MODE == MODE_FORWARD) {
       for (int a = T.lane; a < L.nu; a += G)
         T.w[L.o_ctrl + a] = T.m->step_kind == MMZ_STEP_TELEPORT ? 0.f : A.action[(size_t)env * L.nu + a];
@@ -321,7 +353,9 @@ __global__ void maze_kernel(const __grid_constant__ KArgs A) {
       if (A.mask == nullptr || A.mask[env]) {
         nreset += 1;
         t = 0;
-        T.reset_env(L, A.seed, A.env_offset + env, nreset, true);
+        T.reset_state(L, A.seed, A.env_offset + env, nreset, true);
+        T.kinematics(L);
+        T.latch_objpos(L);
         if (T.lane == 0) { A.counters[env] = 0; A.counters[A.npad + env] = nreset; }
         if (A.obs) T.write_obs(L, A.obs + (size_t)env * L.obs_dim, obs_s, 0);
       }

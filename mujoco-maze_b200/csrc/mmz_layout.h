@@ -37,7 +37,8 @@ enum {
 // per joint-limit row
 enum { R_DOF = 0, R_SIGN = 1, R_D = 2, R_AREF = 3, R_JAR = 4, R_JV = 5, R_STRIDE = 7 };
 // per-env integer counters (stored in the float workspace)
-enum { N_CON = 0, N_LIM = 1, N_ITER = 2, N_OVERFLOW = 3, N_CNT = 4 };
+enum { N_CON = 0, N_LIM = 1, N_ITER = 2, N_OVERFLOW = 3,
+       N_ITER_SUM = 4, N_LS_SUM = 5, N_CON_MAX = 6, N_CAPPED = 7, N_CNT = 8 };  // 4..7: accumulated over one env-step
 
 struct Derived {            // appended to the model blob in device memory
   int32_t anc[MMZ_MAXBODY];  // bit a set in anc[b]: body a is b or an ancestor of b
@@ -45,6 +46,8 @@ struct Derived {            // appended to the model blob in device memory
   int32_t nboxg;
   int32_t nlev;              // number of tree levels
   int32_t pad[2];
+  float ident[9];            // identity rotation (static maze boxes)
+  float padf[3];
 };
 
 struct Layout {

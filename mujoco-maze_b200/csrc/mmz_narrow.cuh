@@ -71,15 +71,11 @@ MMZ_DI float box_excess_deriv(const float* a, const float* b, float t, const flo
   return g;
 }
 
-// capsule (segment p0-p1, radius r) against a box: both end caps when both are within the margin,
-// otherwise one contact at the segment point nearest the box (root of the monotone
-// piecewise-linear derivative of the squared distance along the segment).
-MMZ_DI int capsule_box(const float* p0, const float* p1, float r, const float* bc, const float* bR, const float* h,
-                       float margin, RawContact* out) {
-  RawContact c0, c1;
-  int n0 = sphere_box(p0, r, bc, bR, h, margin, &c0);
-  int n1 = sphere_box(p1, r, bc, bR, h, margin, &c1);
-  if (n0 && n1) { out[0] = c0; out[1] = c1; return 2; }
+// Capsule (segment p0-p1) against a box: parameter t in [0,1] of the segment point nearest the box,
+// the root of the monotone piecewise-linear derivative of the squared distance along the segment.
+// The caller probes both end caps first (two contacts when both are within the margin) and falls
+// back to a single sphere_box at this point (mmz_dyn.cuh: collision).
+MMZ_DI float capsule_nearest(const float* p0, const float* p1, const float* bc, const float* bR, const float* h) {
   float a[3], b[3], rel[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) rel[k] = p0[k] - bc[k];
@@ -87,31 +83,26 @@ MMZ_DI int capsule_box(const float* p0, const float* p1, float r, const float* b
 #pragma unroll
   for (int k = 0; k < 3; k++) rel[k] = p1[k] - p0[k];
   matT_vec(b, bR, rel);
-  float glo = box_excess_deriv(a, b, 0.f, h), ghi = box_excess_deriv(a, b, 1.f, h), ts;
-  if (glo > 0.f) ts = 0.f;
-  else if (ghi <= 0.f) ts = 1.f;
-  else {
-    float tlo = 0.f, thi = 1.f;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      if (fabsf(b[k]) > kMinVal) {
-#pragma unroll
-        for (int s = -1; s <= 1; s += 2) {
-          float t = (s * h[k] - a[k]) / b[k];
-          if (t > 0.f && t < 1.f) {
-            float g = box_excess_deriv(a, b, t, h);
-            if (g <= 0.f) { if (t > tlo) { tlo = t; glo = g; } }
-            else if (t < thi) { thi = t; ghi = g; }
-          }
-        }
+  float glo = box_excess_deriv(a, b, 0.f, h), ghi = box_excess_deriv(a, b, 1.f, h);
+  if (glo > 0.f) return 0.f;
+  if (ghi <= 0.f) return 1.f;
+  float tlo = 0.f, thi = 1.f;
+#pragma unroll 1
+  for (int c = 0; c < 6; c++) {
+    const int k = c >> 1;
+    const float bk = (k == 0) ? b[0] : (k == 1 ? b[1] : b[2]);
+    const float ak = (k == 0) ? a[0] : (k == 1 ? a[1] : a[2]);
+    const float hk = (k == 0) ? h[0] : (k == 1 ? h[1] : h[2]);
+    if (fabsf(bk) > kMinVal) {
+      float t = (((c & 1) ? hk : -hk) - ak) / bk;
+      if (t > 0.f && t < 1.f) {
+        float g = box_excess_deriv(a, b, t, h);
+        if (g <= 0.f) { if (t > tlo) { tlo = t; glo = g; } }
+        else if (t < thi) { thi = t; ghi = g; }
       }
     }
-    ts = (ghi - glo) > kMinVal ? tlo + (-glo) * (thi - tlo) / (ghi - glo) : tlo;
   }
-  float ps[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) ps[k] = p0[k] + ts * (p1[k] - p0[k]);
-  return sphere_box(ps, r, bc, bR, h, margin, out);
+  return (ghi - glo) > kMinVal ? tlo + (-glo) * (thi - tlo) / (ghi - glo) : tlo;
 }
 
 // box against box: separating-axis search, then face clipping or an edge-edge point.

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_PKG_ROOT, "libmmz.so")
 MMZ_DONE, MMZ_TRUNCATED, MMZ_UNSTABLE = 1, 2, 4
 MMZ_AUTO_RESET = 1
 LAYOUT_ENV_MAJOR, LAYOUT_SOA = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 
@@ -47,6 +47,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "mmz_dims": ([vp, ip, ip, ip, ip, ip], i32),
         "mmz_kernel_config": ([vp, ip, ip, ip, ip, ip], i32),
         "mmz_set_env_offset": ([vp, i32], i32),
+        "mmz_set_step_diag": ([vp, vp], i32),
         "mmz_reset": ([vp, vp, u64, vp, vp], i32),
         "mmz_step": ([vp, vp, vp, vp, vp, vp, vp], i32),
         "mmz_step_host": ([vp, vp, vp, vp, vp, vp, vp], i32),
@@ -70,7 +71,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = (
-    "mmz_create", "mmz_dims", "mmz_kernel_config", "mmz_set_env_offset", "mmz_reset", "mmz_step", "mmz_step_host", "mmz_observe", "mmz_get_state",
+    "mmz_create", "mmz_dims", "mmz_kernel_config", "mmz_set_env_offset", "mmz_set_step_diag", "mmz_reset", "mmz_step", "mmz_step_host", "mmz_observe", "mmz_get_state",
     "mmz_set_state", "mmz_forward", "mmz_launch_count", "mmz_last_error", "mmz_destroy", "mmz_abi_version",
 )
 
@@ -183,6 +184,13 @@ class BatchedSim:
         diag = t.empty((self.n, 4), dtype=t.int32, device=self.device)
         self._check(self.lib.mmz_forward(self._h, a.data_ptr(), qacc.data_ptr(), diag.data_ptr(), self._stream()))
         return qacc, diag
+
+    def enable_step_diag(self, on: bool = True):
+        """Per-env solver diagnostics of every following step: [N, 4] int32 (see include/mmz.h)."""
+        t = self.torch
+        self.step_diag = t.zeros((self.n, 4), dtype=t.int32, device=self.device) if on else None
+        self._check(self.lib.mmz_set_step_diag(self._h, _ptr(self.step_diag)))
+        return self.step_diag
 
     @property
     def launch_count(self) -> int:

@@ -156,8 +156,12 @@ def test_step_parity(env_id, torch_cuda, oracle_lib):
                  qvel_err_max=float(ev.max()), qvel_err_p99=float(np.quantile(ev.max(1), 0.99)), qvel_err_median=float(np.median(ev.max(1))),
                  obs_err_max=float(eo.max()), reward_err_max=float(er.max()), done_mismatch=int((done != rbits).sum()),
                  unstable_gpu=int(((done & 4) != 0).sum()), unstable_oracle=int(((rbits & 4) != 0).sum()))
+    worst = np.argsort(-ev.max(1))[:5]
+    stats["worst"] = [dict(env=int(i), dof=int(ev[i].argmax()), gpu_qvel=v1[i].tolist(), oracle_qvel=rv[i].tolist(),
+                           qpos0=q[i].tolist(), qvel0=v[i].tolist(), action=a[i].tolist(), err=float(ev[i].max()))
+                      for i in worst if ev[i].max() > 1e-4]
     _dump("step_" + env_id, stats)
-    print(stats)
+    print({k: v for k, v in stats.items() if k != "worst"})
     assert (t1 == t0 + 1).all()
     good = ev.max(1) <= 1e-3  # envs whose active set did not flip between fp32 and fp64
     assert good.mean() >= 0.97, stats
@@ -254,14 +258,14 @@ def test_state_roundtrip_and_layouts(torch_cuda):
     q1, v1, t1 = sim.get_state()
     q2, v2, _ = sim.get_state(LAYOUT_SOA)
     torch.cuda.synchronize()
-    qn = q.copy()
-    assert np.abs(q1.cpu().numpy() - qn.astype(np.float32)).max() == 0
+    # set_state -> mj_forward normalises the free-joint quaternion in place (as MuJoCo does): round-off only
+    assert np.abs(q1.cpu().numpy() - q.astype(np.float32)).max() < 1e-6
     assert np.abs(v1.cpu().numpy() - v.astype(np.float32)).max() == 0
     assert (t1.cpu().numpy() == t).all()
     assert torch.equal(q2.T.contiguous(), q1) and torch.equal(v2.T.contiguous(), v1)
     sim.set_state(q2, v2, None, layout=LAYOUT_SOA)
     q3, v3, t3 = sim.get_state()
-    assert torch.equal(q3, q1) and torch.equal(v3, v1) and torch.equal(t3, t1)
+    assert (q3 - q1).abs().max().item() < 1e-6 and torch.equal(v3, v1) and torch.equal(t3, t1)
     # observed block position follows the state that was set (set_state -> mj_forward)
     obs = sim.observe().cpu().numpy()
     want = np.asarray(model.body_pos)[int(model.obj_body[0])][:2] + q[:, 15:17]
@@ -301,8 +305,9 @@ def test_truncation_and_auto_reset(torch_cuda):
     from mujoco_maze.backend import BatchedSim
 
     torch = torch_cuda
-    model = make_model("PointUMaze-v0")
     n = 64
+    model = make_model("PointUMaze-v0", num_envs=n)  # batched envs count TimeLimit steps inside the kernel
+    assert int(model.max_episode_steps) == 1000
     sim = BatchedSim(model, n, auto_reset=True)
     sim.reset(seed=1)
     q, v, t = sim.get_state()
