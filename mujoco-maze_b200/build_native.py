@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libmmz.so")
-INSTANCES = ((8, 4), (8, 8), (16, 16), (32, 20))
+# (lanes per env, padded nv, FEAT bits: 1 box geoms, 2 fluid) - keep in step with MMZ_INSTANCES in csrc/mmz_api.cu
+INSTANCES = ((8, 4, 1), (8, 4, 3), (8, 8, 2), (8, 8, 3), (16, 16, 0), (16, 16, 1), (16, 16, 3), (32, 20, 3))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -49,11 +50,11 @@ def build(force: bool = False, verbose: bool = True) -> str:
     objs.append(api_o)
     if force or _stale(api_o, hdrs + [os.path.join(CSRC, "mmz_api.cu")]):
         jobs.append(([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "mmz_api.cu"), "-o", api_o], api_o + ".log"))
-    for g, nvp in INSTANCES:
-        o = os.path.join(OBJ, f"mmz_inst_{g}_{nvp}.o")
+    for g, nvp, feat in INSTANCES:
+        o = os.path.join(OBJ, f"mmz_inst_{g}_{nvp}_{feat}.o")
         objs.append(o)
         if force or _stale(o, hdrs + [os.path.join(CSRC, "mmz_inst.cu")]):
-            jobs.append(([nvcc, *NVCC_FLAGS, f"-DMMZ_G={g}", f"-DMMZ_NVP={nvp}", "-c",
+            jobs.append(([nvcc, *NVCC_FLAGS, f"-DMMZ_G={g}", f"-DMMZ_NVP={nvp}", f"-DMMZ_FEAT={feat}", "-c",
                           os.path.join(CSRC, "mmz_inst.cu"), "-o", o], o + ".log"))
     if jobs:
         if verbose:

@@ -37,11 +37,26 @@ typedef mmz::kernel_fn kernel_fn;
 
 }  // namespace
 
+// kernel instances (one translation unit each, see build_native.py INSTANCES)
+#define MMZ_INSTANCES(X) X(8, 4, 1) X(8, 4, 3) X(8, 8, 2) X(8, 8, 3) X(16, 16, 0) X(16, 16, 1) X(16, 16, 3) X(32, 20, 3)
+namespace mmz {
+#define MMZ_DECL(g, nvp, feat) kernel_fn get_kernel_##g##_##nvp##_##feat(int mode);
+MMZ_INSTANCES(MMZ_DECL)
+#undef MMZ_DECL
+kernel_fn get_kernel(int g, int nvp, int feat, int mode) {
+#define MMZ_PICK(G_, NVP_, FEAT_) if (g == G_ && nvp == NVP_ && feat == FEAT_) return get_kernel_##G_##_##NVP_##_##FEAT_(mode);
+  MMZ_INSTANCES(MMZ_PICK)
+#undef MMZ_PICK
+  return nullptr;
+}
+}  // namespace mmz
+
 struct mmz_env {
   int device = 0;
   int n = 0, npad = 0;
   unsigned flags = 0;
   int G = 32, NVP = 20;  // kernel instance
+  int feat = 0;          // FEAT_* bits the instance was compiled with
   int tpb = 128;         // threads per block
   int smem_bytes = 0;
   int envs_per_sm = 0;
@@ -71,10 +86,7 @@ void make_layout(const mmz_model& m, int G, int NVP, int maxcon, Layout* out) {
   L.obs_dim = m.obs_dim;
   L.ldm = m.nv | 1;
   L.maxcon = maxcon;
-  int nlimited = 0;
-  for (int j = 0; j < m.njnt; j++) nlimited += m.jnt_limited[j] ? 1 : 0;
-  L.maxlim = 2 * nlimited;
-  L.cstride = (C_J + 3 * m.nv) | 1;
+  L.cstride = C_STRIDE;
   L.nstate = m.nq + 2 * m.nv + 3 * m.nobj;
   int o = 0;
   auto take = [&](int n) { int r = o; o += n; return r; };
@@ -90,12 +102,9 @@ void make_layout(const mmz_model& m, int G, int NVP, int maxcon, Layout* out) {
   // composite inertias are dead once M is built; the RNE velocity / acceleration arrays reuse them
   L.o_ic = take(12 * L.nb); L.o_vel = L.o_ic; L.o_acc = L.o_ic + 6 * L.nb;
   L.o_frc = take(6 * L.nb); L.o_fsub = take(6 * L.nb);
-  L.o_M = take(L.nv * L.ldm); L.o_H = take(L.nv * L.ldm);
-  L.o_bias = take(L.nv); L.o_passive = take(L.nv); L.o_smooth = take(L.nv); L.o_qacc_smooth = take(L.nv);
-  L.o_qacc = take(L.nv); L.o_grad = take(L.nv); L.o_dir = take(L.nv); L.o_tmp = take(L.nv);
-  L.o_col = take(2 * NVP);
+  L.o_M = take(L.nv * L.ldm);
+  L.o_smooth = take(L.nv); L.o_qacc = take(L.nv); L.o_dir = take(L.nv);
   L.o_con = take(L.maxcon * L.cstride);
-  L.o_lim = take((L.maxlim > 0 ? L.maxlim : 1) * R_STRIDE);
   L.o_cnt = take(N_CNT);
   L.o_objpos = take(3 * L.nobj > 0 ? 3 * L.nobj : 1);
   L.o_obs = take(L.obs_dim);
@@ -150,15 +159,14 @@ int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s) {
   A.flags = h->flags;
   A.env_offset = h->env_offset;
   int epb = h->tpb / h->G;
-  int blocks = (h->n + epb - 1) / epb;
+  int blocks = (h->npad + epb - 1) / epb;  // padding environments run too (warp-uniform control flow)
   h->fn[mode]<<<blocks, h->tpb, h->smem_bytes, s>>>(A);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return MMZ_OK;
 }
 
-template <int G, int NVP>
-int configure(mmz_env* h) {
+int configure(mmz_env* h, int G, int NVP) {
   h->G = G;
   h->NVP = NVP;
   // contact capacity: generous for box geoms (up to 8 points per box pair), 16 otherwise
@@ -172,9 +180,18 @@ int configure(mmz_env* h) {
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
   const int model_smem = round_up(h->L.model_bytes, 128);
   int best_tpb = 0, best_envs = 0, best_smem = 0;
-  for (int mode = 0; mode < 5; mode++) h->fn[mode] = mmz::get_kernel<G, NVP>(mode);
-  const int cands[] = {256, 128, 64, 32};
-  for (int tpb : cands) {
+  // features this model needs; an instance compiled without the unused ones is preferred
+  int feat = 0;
+  if (nbox) feat |= FEAT_BOX;
+  if (h->hm.density > 0.f || h->hm.viscosity > 0.f) feat |= FEAT_FLUID;
+  if (!mmz::get_kernel(G, NVP, feat, 0)) feat = FEAT_ALL;
+  h->feat = feat;
+  for (int mode = 0; mode < 5; mode++) {
+    h->fn[mode] = mmz::get_kernel(G, NVP, feat, mode);
+    if (!h->fn[mode]) return fail(MMZ_ERR_CAPACITY, "no kernel instance for G=%d NVP=%d", G, NVP);
+  }
+  // block size: any whole number of warps up to the launch bound; keep the one with most resident envs
+  for (int tpb = 256; tpb >= 32; tpb -= 32) {
     if (tpb < G) continue;
     int smem = model_smem + (tpb / G) * h->L.stride * 4;
     if (smem > dev_smem) continue;
@@ -218,10 +235,10 @@ int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, u
   auto bail = [&](int code) { mmz_destroy(h); return code; };
   if (cudaSetDevice(device) != cudaSuccess) return bail(fail(MMZ_ERR_CUDA, "cudaSetDevice(%d) failed", device));
   const int nv = h->hm.nv;
-  if (nv <= 4 && h->hm.nbody <= 8 && h->hm.ngeom <= 8) rc = configure<8, 4>(h);
-  else if (nv <= 8) rc = configure<8, 8>(h);
-  else if (nv <= 16) rc = configure<16, 16>(h);
-  else rc = configure<32, 20>(h);
+  if (nv <= 4 && h->hm.nbody <= 8 && h->hm.ngeom <= 8) rc = configure(h, 8, 4);
+  else if (nv <= 8) rc = configure(h, 8, 8);
+  else if (nv <= 16) rc = configure(h, 16, 16);
+  else rc = configure(h, 32, 20);
   if (rc != MMZ_OK) return bail(rc);
   // device copy of the constants: model + derived tables, padded to a multiple of 16 bytes
   {

@@ -17,47 +17,70 @@
 // each at its own place in a long program), so every large routine has exactly ONE call site
 // (forward, the Cholesky, sphere_box, ...) and loops with big bodies are kept rolled.
 #pragma once
+#include <cstdio>
+
 #include "mmz_layout.h"
 #include "mmz_narrow.cuh"
 
 namespace mmz {
 
+// Control flow is kept WARP-UNIFORM: the 32/G environments that share a warp run every loop to the
+// warp-wide maximum trip count (the shorter ones predicated off), so all 32 lanes reach every shuffle,
+// ballot and __syncwarp together and the full mask can be used. (With per-group masks the compiler
+// must guard every shuffle with a divergence check and a ~10-instruction collective fallback, which
+// doubled the code size of the step.)
+constexpr unsigned kFull = 0xffffffffu;
+#ifdef MMZ_DEBUG_UNIFORM
+#define MMZ_CONV(id) do { unsigned am_ = __activemask(); if (am_ != kFull && (threadIdx.x & 15) == 0) printf("diverged at %d: active %08x block %d thread %d\n", id, am_, blockIdx.x, threadIdx.x); } while (0)
+#else
+#define MMZ_CONV(id) do {} while (0)
+#endif
+
 template <int G>
-MMZ_DI float gsum(float v, unsigned mask) {
+MMZ_DI float gsum(float v) {  // sum over the group
 #pragma unroll
-  for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off);
+  for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
   return v;
 }
-template <int G>
-MMZ_DI int gmax(int v, unsigned mask) {
+MMZ_DI int wmax(int v) {  // maximum over the whole warp (all groups)
 #pragma unroll
-  for (int off = G / 2; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(mask, v, off));
+  for (int off = 16; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(kFull, v, off));
   return v;
 }
-// inclusive prefix sum over the group; *total = sum over all lanes
+// inclusive prefix sum over the group; *total = sum over the group's lanes
 template <int G>
-MMZ_DI int gscan(int v, int lane, unsigned mask, int* total) {
+MMZ_DI int gscan(int v, int lane, int* total) {
 #pragma unroll
   for (int off = 1; off < G; off <<= 1) {
-    int t = __shfl_up_sync(mask, v, off, G);
+    int t = __shfl_up_sync(kFull, v, off, G);
     if (lane >= off) v += t;
   }
-  *total = __shfl_sync(mask, v, G - 1, G);
+  *total = __shfl_sync(kFull, v, G - 1, G);
   return v;
 }
 
 constexpr int kMaxNewton = 24;
+// optional features a kernel instance is compiled with (the rest of the code is absent from it:
+// the step is instruction-fetch sensitive, so a model only pays for what it uses)
+enum { FEAT_BOX = 1,    // box geoms on moving bodies (Point's arrow, movable blocks): box-box, plane-box
+       FEAT_FLUID = 2,  // fluid drag (Swimmer: density / viscosity)
+       FEAT_ALL = 3 };
 constexpr int kMaxLineSearch = 24;
 
-template <int G, int NVP>
+template <int G, int NVP, int FEAT>
 struct Env {
   const mmz_model* m;  // shared memory
   const Derived* dv;   // shared memory
   float* w;            // this environment's workspace (shared memory)
   int lane;            // 0..G-1
-  unsigned gmask;      // lanes of this group inside the warp
+  int gshift;          // bit position of this group's lane 0 inside the warp
 
-  MMZ_DI void sync() const { __syncwarp(gmask); }
+  MMZ_DI void sync() const { __syncwarp(); }
+  // ballot restricted to this group's lanes (bit i = lane i of the group)
+  MMZ_DI unsigned gballot(bool p) const {
+    const unsigned b = __ballot_sync(kFull, p);
+    return G == 32 ? b : ((b >> gshift) & ((1u << (G % 32)) - 1u));
+  }
   MMZ_DI int* cnt(const Layout& L) const { return reinterpret_cast<int*>(w + L.o_cnt); }
   // All spatial quantities (cdof, inertias, wrenches, contact Jacobians) are taken about the
   // origin of body 0 instead of the world origin: the physics is translation invariant, and in
@@ -405,8 +428,8 @@ struct Env {
     const float* cdof = w + L.o_cdof;
     const float* qvel = w + L.o_qvel;
     const float* fsub = w + L.o_fsub;
-    const bool fluid = m->density > 0.f || m->viscosity > 0.f;
-    if (fluid) fluid_forces(L);  // wrenches land in frc, which the subtree sums have consumed
+    const bool fluid = (FEAT & FEAT_FLUID) && (m->density > 0.f || m->viscosity > 0.f);
+    if constexpr ((FEAT & FEAT_FLUID) != 0) { if (fluid) fluid_forces(L); }  // wrenches land in frc, which the subtree sums have consumed
     const float* sf = w + L.o_frc;
 #pragma unroll 1
     for (int d = lane; d < L.nv; d += G) {
@@ -521,8 +544,8 @@ struct Env {
         nj = max(1, j1 - j0 + 1);
         ncell = max(0, j1 - j0 + 1) * max(0, i1 - i0 + 1);
       }
-      const int maxcell = gmax<G>(ncell, gmask);
-      const int ncand = 1 + nslot * maxcell + dv->nboxg;
+      const int maxcell = wmax(ncell);  // warp-uniform candidate count
+      const int ncand = 1 + nslot * maxcell + ((FEAT & FEAT_BOX) ? dv->nboxg : 0);
 #pragma unroll 1
       for (int cand = 0; cand < ncand; cand++) {
         RawContact r0, r1;
@@ -571,7 +594,7 @@ struct Env {
                 box = true;
               }
             }
-          } else {  // box geoms on other moving bodies; geom1 = this geom, geom2 = box
+          } else if (FEAT & FEAT_BOX) {  // box geoms on other moving bodies; geom1 = this geom, geom2 = box
             int gb = dv->boxg[cand - 1 - nslot * maxcell];
             if (moving_pair_ok(g, gb)) {
               margin = fmaxf(gmarg, m->geom_margin[gb]);
@@ -608,9 +631,8 @@ struct Env {
             n = (n0 && n1) ? 2 : n0;  // after the third probe n1 == 0 and n0 is the nearest-point result
           }
         }
-        unsigned any = __ballot_sync(gmask, n > 0);
-        if (!any) continue;
-        int total, incl = gscan<G>(n, lane, gmask, &total);  // keeps the contact order deterministic
+        if (!__any_sync(kFull, n > 0)) continue;
+        int total, incl = gscan<G>(n, lane, &total);  // keeps the contact order deterministic
         int base = ncon + incl - n;
         if (n > 0 && base < L.maxcon) write_contact(L, base, r0, b1, b2, iw, g, other);
         if (n > 1 && base + 1 < L.maxcon) write_contact(L, base + 1, r1, b1, b2, iw, g, other);
@@ -621,11 +643,13 @@ struct Env {
     if (lane == 0) { cn[N_CON] = ncon; cn[N_OVERFLOW] = overflow ? 1 : 0; }
     sync();
     // ---- box geoms (Point's arrow, movable blocks): few, handled by one lane each in order
+    if constexpr ((FEAT & FEAT_BOX) != 0) {
 #pragma unroll 1
-    for (int k = 0; k < dv->nboxg; k++) {
-      int g = dv->boxg[k];
-      if (lane == 0 && ((m->geom_contype[g] | m->geom_conaffinity[g]) & 1)) box_geom_contacts(L, g, k);
-      sync();
+      for (int k = 0; k < dv->nboxg; k++) {
+        int g = dv->boxg[k];
+        if (lane == 0 && ((m->geom_contype[g] | m->geom_conaffinity[g]) & 1)) box_geom_contacts(L, g, k);
+        sync();
+      }
     }
   }
 
@@ -715,349 +739,373 @@ struct Env {
     *kr = k * imp * (pos - margin);
   }
 
+  // Joint limits: dof d's own limit rows live in lane d's registers (a limit row is +-e_d, so
+  // nothing about it needs to be shared): side 0 = lower (J = +1), side 1 = upper (J = -1).
+  // limD[s] = 0 marks an inactive side. Contacts: one lane per contact turns the narrow-phase
+  // record into D, aref[4] and the signed dof masks. J qvel comes from the body velocities the
+  // bias pass has just computed (point velocity of body2 minus body1), not from a Jacobian.
+  float limD[2], limA[2];
+
   MMZ_DI void make_constraints(const Layout& L) {
     int* cn = cnt(L);
     const float* qpos = w + L.o_qpos;
     const float* qvel = w + L.o_qvel;
-    const float* cdof = w + L.o_cdof;
     const int ncon = cn[N_CON];
-    // One pass over "row sources": indices [0, 2 nj) are (joint, side) limit candidates, the rest
-    // are contacts, so row_params / impedance have a single call site. Limit rows are compacted
-    // in (joint, lower-then-upper) order with a group scan.
-    int nlim = 0;
-    const int nsrc = 2 * L.nj + ncon;
+    limD[0] = limD[1] = 0.f; limA[0] = limA[1] = 0.f;
+    // one loop over "row sources" so that row_params / impedance have a single call site:
+    // pass 0, 1 = the two limit sides of this lane's dof, passes >= 2 = contacts lane, lane + G, ...
+    const int jl = lane < L.nv ? m->dof_jnt[lane] : 0;
+    const bool limited = lane < L.nv && m->jnt_limited[jl] && m->jnt_type[jl] >= MMZ_JNT_SLIDE;
+    const int npass = 2 + (wmax(ncon) + G - 1) / G;
 #pragma unroll 1
-    for (int base = 0; base < nsrc; base += G) {
-      const int idx = base + lane;
-      const bool is_lim = idx < 2 * L.nj, is_con = !is_lim && idx < nsrc;
-      // ---- limit candidate
-      int j = idx >> 1, side = idx & 1, n = 0, d = 0;
-      float pos = 0.f, margin = 0.f, diag = 0.f, mu = 0.f;
+    for (int pass = 0; pass < npass; pass++) {
+      float pos = 0.f, margin = 0.f, diag = 0.f, mu = 0.f, jv0 = 0.f, jv1 = 0.f, jv2 = 0.f;
       const float *solref = m->wall_solref, *solimp = m->wall_solimp;
       float* cs = nullptr;
-      float jv0 = 0.f, jv1 = 0.f, jv2 = 0.f;
-      if (is_lim && m->jnt_limited[j]) {
-        float q = qpos[m->jnt_qadr[j]];
-        pos = side == 0 ? q - m->jnt_range[j][0] : m->jnt_range[j][1] - q;
-        margin = m->jnt_margin[j];
-        n = pos < margin;
-        d = m->jnt_dadr[j];
-        diag = m->dof_invweight0[d];
-        solref = m->jnt_solref[j]; solimp = m->jnt_solimp[j];
-      }
-      if (is_con) {  // frame Jacobian of the relative point velocity (body2 - body1)
-        cs = w + L.o_con + (idx - 2 * L.nj) * L.cstride;
-        float* J = cs + C_J;
-        float cp[3], fr[9];
+      bool on = false;
+      if (pass < 2) {
+        if (limited) {
+          float q = qpos[m->jnt_qadr[jl]];
+          pos = pass == 0 ? q - m->jnt_range[jl][0] : m->jnt_range[jl][1] - q;
+          margin = m->jnt_margin[jl];
+          on = pos < margin;
+          diag = m->dof_invweight0[lane];
+          solref = m->jnt_solref[jl]; solimp = m->jnt_solimp[jl];
+        }
+      } else {
+        const int c = (pass - 2) * G + lane;
+        if (c < ncon) {
+          on = true;
+          cs = w + L.o_con + c * L.cstride;
+          float cp[3], v[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int k = 0; k < 3; k++) cp[k] = cs[C_POS + k] - w[L.o_xpos + k];
-#pragma unroll
-        for (int k = 0; k < 9; k++) fr[k] = cs[C_FRAME + k];
-        int b1 = __float_as_int(cs[C_BODY1]), b2 = __float_as_int(cs[C_BODY2]);
-        int mask1 = b1 >= 0 ? m->body_dofmask[b1] : 0, mask2 = b2 >= 0 ? m->body_dofmask[b2] : 0;
-#pragma unroll 1
-        for (int dd = 0; dd < L.nv; dd++) {
-          float s = (float)(mask2 >> dd & 1) - (float)(mask1 >> dd & 1);
-          float jn = 0.f, jt1 = 0.f, jt2 = 0.f;
-          if (s != 0.f) {
-            const float* cd = cdof + 6 * dd;
+          for (int k = 0; k < 3; k++) { cp[k] = cs[C_POS + k] - w[L.o_xpos + k]; cs[C_POS + k] = cp[k]; }
+          const int b1 = __float_as_int(cs[C_BODY1]), b2 = __float_as_int(cs[C_BODY2]);
+          const int mask1 = b1 >= 0 ? m->body_dofmask[b1] : 0, mask2 = b2 >= 0 ? m->body_dofmask[b2] : 0;
+          if (b2 >= 0) {
+            const float* bv = w + L.o_vel + 6 * b2;
             float wxp[3];
-            cross3(wxp, cd, cp);
-            float v[3] = {cd[3] + wxp[0], cd[4] + wxp[1], cd[5] + wxp[2]};
-            jn = s * dot3(fr, v); jt1 = s * dot3(fr + 3, v); jt2 = s * dot3(fr + 6, v);
-            float qv = qvel[dd];
-            jv0 += jn * qv; jv1 += jt1 * qv; jv2 += jt2 * qv;
+            cross3(wxp, bv, cp);
+#pragma unroll
+            for (int k = 0; k < 3; k++) v[k] += bv[3 + k] + wxp[k];
           }
-          J[dd] = jn; J[L.nv + dd] = jt1; J[2 * L.nv + dd] = jt2;
+          if (b1 >= 0) {
+            const float* bv = w + L.o_vel + 6 * b1;
+            float wxp[3];
+            cross3(wxp, bv, cp);
+#pragma unroll
+            for (int k = 0; k < 3; k++) v[k] -= bv[3 + k] + wxp[k];
+          }
+          jv0 = dot3(cs + C_FRAME, v); jv1 = dot3(cs + C_FRAME + 3, v); jv2 = dot3(cs + C_FRAME + 6, v);
+          mu = cs[C_MU];
+          pos = cs[C_DIST]; margin = cs[C_MARGIN]; diag = cs[C_INVW] * (1.f + mu * mu);
+          solref = cs + C_SOLREF; solimp = cs + C_SOLIMP;
+          cs[C_MPOS] = __int_as_float(mask2 & ~mask1);
+          cs[C_MNEG] = __int_as_float(mask1 & ~mask2);
         }
-        mu = cs[C_MU];
-        pos = cs[C_DIST]; margin = cs[C_MARGIN]; diag = cs[C_INVW] * (1.f + mu * mu);
-        solref = cs + C_SOLREF; solimp = cs + C_SOLIMP;
       }
-      int slot = 0;
-      if (base < 2 * L.nj) {  // chunks that contain limit candidates
-        if (__ballot_sync(gmask, n > 0)) {
-          int total;
-          slot = nlim + gscan<G>(n, lane, gmask, &total) - n;
-          nlim = min(nlim + total, L.maxlim);
-        }
-      }
-      if ((n && slot < L.maxlim) || is_con) {
+      if (on) {
         float D, kr, bb;
         row_params(solref, solimp, pos, margin, diag, &D, &kr, &bb);
-        if (is_con) {
+        if (pass < 2) {
+          const float sign = pass == 0 ? 1.f : -1.f;
+          limD[pass] = D;
+          limA[pass] = -bb * sign * qvel[lane] - kr;
+        } else {
           // all edges of the pyramid share R = 2 mu^2 R_first
-          cs[C_DIST] = 1.f / fmaxf(kMinVal, 2.f * mu * mu / D);
+          cs[C_D] = 1.f / fmaxf(kMinVal, 2.f * mu * mu / D);
           cs[C_AREF + 0] = -bb * (jv0 + mu * jv1) - kr;
           cs[C_AREF + 1] = -bb * (jv0 - mu * jv1) - kr;
           cs[C_AREF + 2] = -bb * (jv0 + mu * jv2) - kr;
           cs[C_AREF + 3] = -bb * (jv0 - mu * jv2) - kr;
-        } else {
-          float sign = side == 0 ? 1.f : -1.f;
-          float* r = w + L.o_lim + slot * R_STRIDE;
-          r[R_DOF] = __int_as_float(d);
-          r[R_SIGN] = sign;
-          r[R_D] = D;
-          r[R_AREF] = -bb * sign * qvel[d] - kr;
         }
       }
     }
+    const int nlim = __popc(gballot(limD[0] > 0.f)) + __popc(gballot(limD[1] > 0.f));
     if (lane == 0) cn[N_LIM] = nlim;
     sync();
   }
 
-  // ---------------------------------------------------------------- dense Cholesky in shared memory
-  // Lane i holds row i of a symmetric positive-definite matrix in registers; the rows are stored to
-  // shared memory and factored in place by a ROLLED right-looking loop (lanes <-> rows): on return L
-  // (lower) is at Lsm[i*ldm + k], k <= i. Rolled on purpose: a fully unrolled register version is
-  // ~1500 instructions of straight-line code that every Newton iteration has to fetch.
-  MMZ_DI void chol_rows(const Layout& L, const float (&row)[NVP], float* Lsm) {
-    const int nv = L.nv, ld = L.ldm;
-    float* my = Lsm + lane * ld;
-    if (lane < nv) {
+  // ---------------------------------------------------------------- dense solve in registers
+  // Lane i holds row i of the symmetric positive-definite H (full row, NVP registers) and element i
+  // of the right-hand side. Gaussian elimination without pivoting, the pivot row broadcast by
+  // shuffles, then back substitution on the frozen upper rows: no shared memory, no barriers.
+  // Rows >= nv are identity padding. Returns x = H^-1 rhs (element `lane`).
+  MMZ_DI float elim_solve(float (&h)[NVP], float rhs, int nv) const {
+    float invd = 1.f;
 #pragma unroll
-      for (int k = 0; k < NVP; k++)
-        if (k <= lane) my[k] = row[k];
-    }
-    sync();
-#pragma unroll 1
-    for (int j = 0; j < nv; j++) {
-      const float piv = fmaxf(Lsm[j * ld + j], kMinVal);
-      const float inv = rsqrtf(piv);
-      float lij = 0.f;
-      if (lane >= j && lane < nv) {
-        lij = (lane == j) ? piv * inv : my[j] * inv;
-        my[j] = lij;
+    for (int j = 0; j < NVP; j++) {
+      if (j < nv) {
+        const float piv = fmaxf(__shfl_sync(kFull, h[j], j, G), kMinVal);
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv));
+        inv = inv * (2.f - piv * inv);
+        const float rj = __shfl_sync(kFull, rhs, j, G);
+        const float f = (lane > j) ? h[j] * inv : 0.f;
+        if (lane == j) invd = inv;
+        rhs -= f * rj;
+#pragma unroll
+        for (int k = j + 1; k < NVP; k++) h[k] -= f * __shfl_sync(kFull, h[k], j, G);
       }
-      sync();
-      if (lane > j && lane < nv) {
-#pragma unroll 2
-        for (int k = j + 1; k <= lane; k++) my[k] -= lij * Lsm[k * ld + j];
-      }
-      sync();
     }
+    float x = rhs;
+#pragma unroll
+    for (int j = NVP - 1; j >= 0; j--) {
+      if (j < nv) {
+        const float xj = __shfl_sync(kFull, x * invd, j, G);
+        x = (lane == j) ? xj : ((lane < j) ? x - h[j] * xj : x);
+      }
+    }
+    return x;
   }
-  // x <- (L L^T)^-1 x for the vector held one element per lane
-  MMZ_DI float chol_solve(const Layout& L, const float* Lsm, float x) {
-    const int nv = L.nv;
-    float invd = (lane < nv) ? 1.f / Lsm[lane * L.ldm + lane] : 0.f;
-    float acc = x;
-#pragma unroll 1
-    for (int k = 0; k < nv; k++) {
-      float yk = __shfl_sync(gmask, acc * invd, k, G);
-      if (lane > k && lane < nv) acc -= Lsm[lane * L.ldm + k] * yk;
-      if (lane == k) acc = yk;
-    }
-#pragma unroll 1
-    for (int k = nv - 1; k >= 0; k--) {
-      float xk = __shfl_sync(gmask, acc * invd, k, G);
-      if (lane < k) acc -= Lsm[k * L.ldm + lane] * xk;
-      if (lane == k) acc = xk;
-    }
-    return acc;
+
+  // this lane's column of the contact-frame Jacobian of contact block cs: (J_n, J_t1, J_t2)[lane]
+  MMZ_DI void contact_jac(const float* cs, const float (&cd)[6], float* jn, float* jt1, float* jt2) const {
+    const int mp = __float_as_int(cs[C_MPOS]), mn = __float_as_int(cs[C_MNEG]);
+    const float s = (float)(mp >> lane & 1) - (float)(mn >> lane & 1);
+    float wxp[3];
+    cross3(wxp, cd, cs + C_POS);
+    const float v[3] = {s * (cd[3] + wxp[0]), s * (cd[4] + wxp[1]), s * (cd[5] + wxp[2])};
+    *jn = dot3(cs + C_FRAME, v); *jt1 = dot3(cs + C_FRAME + 3, v); *jt2 = dot3(cs + C_FRAME + 6, v);
   }
 
   // ---------------------------------------------------------------- Newton solver (mj_solNewton)
   //   min_a 1/2 a^T M a - a^T qfrc_smooth + sum_i 1/2 D_i min(0, J_i a - aref_i)^2
-  // Row products J x for the limit rows and the 4 pyramid edges of every contact. which = 0:
-  // jar = J x - aref, with the magnitude of the cancelling terms (for the round-off floor of the
-  // convergence test) parked in the jv slot; which = 1: jv = J x.
-  MMZ_DI void row_products(const Layout& L, const float* x, int nlim, int ncon, int which) {
-    float* lim = w + L.o_lim;
+  // Lanes <-> dofs throughout. Row products J x are lane-local products reduced over the group
+  // (contacts) or purely lane-local (limits). which = 0: x = a, stores jar = J a - aref per edge
+  // and returns the gradient / round-off contributions; which = 1: x = dir, stores jv = J dir.
+  // Contact loops run to ncw, the warp-wide maximum contact count (slots >= ncon are ignored).
+  MMZ_DI void contact_products(const Layout& L, const float (&cd)[6], float x, int ncon, int ncw, int which, float* grad,
+                               float* mag) {
+    float* con = w + L.o_con;
 #pragma unroll 1
-    for (int r = lane; r < nlim; r += G) {
-      float* lr = lim + r * R_STRIDE;
-      float jx = lr[R_SIGN] * x[__float_as_int(lr[R_DOF])];
-      if (which == 0) { lr[R_JAR] = jx - lr[R_AREF]; lr[R_JV] = fabsf(jx) + fabsf(lr[R_AREF]); }
-      else lr[R_JV] = jx;
-    }
-#pragma unroll 1
-    for (int c = lane; c < ncon; c += G) {
-      float* cs = w + L.o_con + c * L.cstride;
-      const float* J = cs + C_J;
-      const float mu = cs[C_MU];
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, sa = 0.f;
-#pragma unroll 2
-      for (int d = 0; d < L.nv; d++) {
-        float xd = x[d], jn = J[d], j1 = J[L.nv + d], j2 = J[2 * L.nv + d];
-        s0 += jn * xd; s1 += j1 * xd; s2 += j2 * xd;
-        sa += (fabsf(jn) + mu * (fabsf(j1) + fabsf(j2))) * fabsf(xd);
+    for (int c = 0; c < ncw; c++) {
+      float* cs = con + c * L.cstride;
+      const bool valid = c < ncon;
+      float jn, jt1, jt2;
+      contact_jac(cs, cd, &jn, &jt1, &jt2);
+      if (!valid) { jn = 0.f; jt1 = 0.f; jt2 = 0.f; }
+      const float mu = valid ? cs[C_MU] : 0.f;
+      float s0 = jn * x, s1 = jt1 * x, s2 = jt2 * x, sa = (fabsf(jn) + mu * (fabsf(jt1) + fabsf(jt2))) * fabsf(x);
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1) {
+        s0 += __shfl_xor_sync(kFull, s0, off);
+        s1 += __shfl_xor_sync(kFull, s1, off);
+        s2 += __shfl_xor_sync(kFull, s2, off);
+        if (which == 0) sa += __shfl_xor_sync(kFull, sa, off);
       }
-      float e0 = s0 + mu * s1, e1 = s0 - mu * s1, e2 = s0 + mu * s2, e3 = s0 - mu * s2;
+      if (!valid) continue;  // no shuffles below
+      const float e0 = s0 + mu * s1, e1 = s0 - mu * s1, e2 = s0 + mu * s2, e3 = s0 - mu * s2;
       if (which == 0) {
-        float a0 = cs[C_AREF], a1 = cs[C_AREF + 1], a2 = cs[C_AREF + 2], a3 = cs[C_AREF + 3];
-        cs[C_JAR + 0] = e0 - a0; cs[C_JAR + 1] = e1 - a1; cs[C_JAR + 2] = e2 - a2; cs[C_JAR + 3] = e3 - a3;
-        cs[C_JV] = sa + fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fmaxf(fabsf(a2), fabsf(a3)));
-      } else {
-        cs[C_JV + 0] = e0; cs[C_JV + 1] = e1; cs[C_JV + 2] = e2; cs[C_JV + 3] = e3;
+        const float r0 = cs[C_AREF], r1 = cs[C_AREF + 1], r2 = cs[C_AREF + 2], r3 = cs[C_AREF + 3];
+        const float j0 = e0 - r0, j1 = e1 - r1, j2 = e2 - r2, j3 = e3 - r3;
+        if (lane == 0) { cs[C_JAR] = j0; cs[C_JAR + 1] = j1; cs[C_JAR + 2] = j2; cs[C_JAR + 3] = j3; }
+        const float a0 = j0 < 0.f, a1 = j1 < 0.f, a2 = j2 < 0.f, a3 = j3 < 0.f;
+        const float D = cs[C_D];
+        // -J^T f with f_k = -D jar_k on the active edges
+        const float f0 = a0 * D * j0, f1 = a1 * D * j1, f2 = a2 * D * j2, f3 = a3 * D * j3;
+        *grad += jn * (f0 + f1 + f2 + f3) + jt1 * (mu * (f0 - f1)) + jt2 * (mu * (f2 - f3));
+        const float bound = sa + fmaxf(fmaxf(fabsf(r0), fabsf(r1)), fmaxf(fabsf(r2), fabsf(r3)));
+        *mag += D * bound * ((a0 + a1 + a2 + a3) * fabsf(jn) + mu * ((a0 + a1) * fabsf(jt1) + (a2 + a3) * fabsf(jt2)));
+      } else if (lane == 0) {
+        cs[C_JV] = e0; cs[C_JV + 1] = e1; cs[C_JV + 2] = e2; cs[C_JV + 3] = e3;
       }
     }
-    sync();
   }
 
   MMZ_DI void solve(const Layout& L, bool warmstart) {
     int* cn = cnt(L);
-    const int nv = L.nv, ncon = cn[N_CON], nlim = cn[N_LIM], nrow = nlim + 4 * ncon;
+    const int nv = L.nv, ncon = cn[N_CON];
+    const int ncw = wmax(ncon);
     float* a = w + L.o_qacc;
     const float* M = w + L.o_M;
-    const float* smooth = w + L.o_smooth;
-    float* H = w + L.o_H;
     float* dir = w + L.o_dir;
-    float* lim = w + L.o_lim;
     float* con = w + L.o_con;
     const bool me = lane < nv;
+    const unsigned limbits = gballot(limD[0] > 0.f || limD[1] > 0.f);  // (collectives are never short-circuited)
+    const bool constrained = ncon > 0 || limbits != 0;
+    float cd[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) cd[k] = me ? w[L.o_cdof + 6 * lane + k] : 0.f;
+    const float sm = me ? w[L.o_smooth + lane] : 0.f;
+    float al = (warmstart && me) ? a[lane] : 0.f;
     if (!warmstart && me) a[lane] = 0.f;
     if (lane == 0) { cn[N_ITER] = 0; cn[N_CON_MAX] = max(cn[N_CON_MAX], ncon); }
     sync();
-    // pass 2k evaluates jar = J a - aref, pass 2k+1 (after the Newton direction is known) jv = J dir:
-    // a single row_products call site serves both
-    float hrow[NVP];
-    float Ma = 0.f, grad = 0.f, sm = 0.f, dr = 0.f;
-    bool stop = false;
+    // `done`: this environment's solve has finished; it keeps executing, predicated off, until every
+    // environment of the warp has (uniform control flow)
+    bool done = false;
 #pragma unroll 1
-    for (int pass = 0; pass < 2 * kMaxNewton && !stop; pass++) {
-      const int it = pass >> 1;
-      if (nrow) row_products(L, (pass & 1) ? dir : a, nlim, ncon, pass & 1);
-      if (!(pass & 1)) {
-        // gradient and Hessian row of this lane's dof; `mag` bounds the round-off of the gradient
-        float mag = 0.f;
-        Ma = 0.f;
+    for (int it = 0; it < kMaxNewton; it++) {
+      // ---- gradient at a; `mag` bounds the round-off of the terms it is the (cancelling) sum of
+      float Ma = 0.f, mag = 0.f;
+      if (me) {
+#pragma unroll 2
+        for (int k = 0; k < nv; k++) { float t = M[lane * L.ldm + k] * a[k]; Ma += t; mag += fabsf(t); }
+      }
+      float grad = Ma - sm, dadd = 0.f;
+      mag += fabsf(sm);
+      float ljar[2];
 #pragma unroll
-        for (int k = 0; k < NVP; k++) {
-          float mk = (me && k < nv) ? M[lane * L.ldm + k] : ((k == lane) ? 1.f : 0.f);
-          hrow[k] = mk;
-          if (k < nv) { float t = mk * a[k]; Ma += t; mag += fabsf(t); }
+      for (int s = 0; s < 2; s++) {
+        const float sign = s == 0 ? 1.f : -1.f;
+        ljar[s] = sign * al - limA[s];
+        if (limD[s] > 0.f && ljar[s] < 0.f) {
+          grad += limD[s] * ljar[s] * sign;  // = -J^T force
+          mag += limD[s] * (fabsf(al) + fabsf(limA[s]));
+          dadd += limD[s];
         }
-        if (!me) { Ma = 0.f; mag = 0.f; }
-        sm = me ? smooth[lane] : 0.f;
-        grad = Ma - sm;
-        mag += fabsf(sm);
-        float dadd = 0.f;
-#pragma unroll 1
-        for (int r = 0; r < nlim; r++) {
-          const float* lr = lim + r * R_STRIDE;
-          float jar = lr[R_JAR];
-          if (jar < 0.f && __float_as_int(lr[R_DOF]) == lane) {
-            grad += lr[R_D] * jar * lr[R_SIGN];  // = -J^T force
-            mag += lr[R_D] * lr[R_JV];
-            dadd += lr[R_D];
-          }
-        }
-#pragma unroll 1
-        for (int c = 0; c < ncon; c++) {
-          const float* cs = con + c * L.cstride;
-          float j0 = cs[C_JAR], j1 = cs[C_JAR + 1], j2 = cs[C_JAR + 2], j3 = cs[C_JAR + 3];
-          float a0 = j0 < 0.f, a1 = j1 < 0.f, a2 = j2 < 0.f, a3 = j3 < 0.f;
-          if (a0 + a1 + a2 + a3 == 0.f) continue;
-          float D = cs[C_DIST], mu = cs[C_MU];
-          const float* J = cs + C_J;
-          float jn = me ? J[lane] : 0.f, jt1 = me ? J[nv + lane] : 0.f, jt2 = me ? J[2 * nv + lane] : 0.f;
-          // -J^T f with f_k = -D jar_k on active edges
-          float f0 = a0 * D * j0, f1 = a1 * D * j1, f2 = a2 * D * j2, f3 = a3 * D * j3;
-          grad += jn * (f0 + f1 + f2 + f3) + jt1 * (mu * (f0 - f1)) + jt2 * (mu * (f2 - f3));
-          mag += D * cs[C_JV] * ((a0 + a1 + a2 + a3) * fabsf(jn) + mu * ((a0 + a1) * fabsf(jt1) + (a2 + a3) * fabsf(jt2)));
-          // H += Jc^T W Jc, W from the active edges
-          float wnn = D * (a0 + a1 + a2 + a3), wn1 = D * mu * (a0 - a1), wn2 = D * mu * (a2 - a3);
-          float w11 = D * mu * mu * (a0 + a1), w22 = D * mu * mu * (a2 + a3);
-          float u0 = wnn * jn + wn1 * jt1 + wn2 * jt2, u1 = wn1 * jn + w11 * jt1, u2 = wn2 * jn + w22 * jt2;
+      }
+      MMZ_CONV(10);
+      contact_products(L, cd, al, ncon, ncw, 0, &grad, &mag);
+      MMZ_CONV(11);
+      // converged when every dof's gradient is at the fp32 round-off level of the terms it is the
+      // (cancelling) sum of. The test is per dof, not on the norm: a light body (movable block,
+      // 2e-4 kg) next to a heavy one would otherwise be left with a large acceleration error.
+      if (gballot(fabsf(grad) > 2e-6f * mag + 1e-30f) == 0) done = true;
+      if (__all_sync(kFull, done)) break;
+      sync();  // the jar values lane 0 stored are read by every lane below
+      // ---- Hessian row of this lane's dof: M + sum over active rows of D J^T J
+      float hrow[NVP];
 #pragma unroll
-          for (int k = 0; k < NVP; k++)
-            if (k < nv) hrow[k] += u0 * J[k] + u1 * J[nv + k] + u2 * J[2 * nv + k];
-        }
+      for (int k = 0; k < NVP; k++) {
+        float mk = (me && k < nv) ? M[lane * L.ldm + k] : 0.f;
+        hrow[k] = (k == lane) ? (me ? mk + dadd : 1.f) : mk;
+      }
+#pragma unroll 1
+      for (int c = 0; c < ncw; c++) {
+        const float* cs = con + c * L.cstride;
+        const bool valid = c < ncon;
+        const float a0 = valid && cs[C_JAR] < 0.f, a1 = valid && cs[C_JAR + 1] < 0.f, a2 = valid && cs[C_JAR + 2] < 0.f,
+                    a3 = valid && cs[C_JAR + 3] < 0.f;
+        const bool act = a0 + a1 + a2 + a3 != 0.f;
+        if (!__any_sync(kFull, act)) continue;
+        float jn, jt1, jt2;
+        contact_jac(cs, cd, &jn, &jt1, &jt2);
+        if (!act) { jn = 0.f; jt1 = 0.f; jt2 = 0.f; }
+        const float D = act ? cs[C_D] : 0.f, mu = act ? cs[C_MU] : 0.f;
+        const float wnn = D * (a0 + a1 + a2 + a3), wn1 = D * mu * (a0 - a1), wn2 = D * mu * (a2 - a3);
+        const float w11 = D * mu * mu * (a0 + a1), w22 = D * mu * mu * (a2 + a3);
+        const float u0 = wnn * jn + wn1 * jt1 + wn2 * jt2, u1 = wn1 * jn + w11 * jt1, u2 = wn2 * jn + w22 * jt2;
 #pragma unroll
         for (int k = 0; k < NVP; k++)
-          if (k == lane) hrow[k] += dadd;
-        // converged when every dof's gradient is at the fp32 round-off level of the terms it is the
-        // (cancelling) sum of. The test is per dof, not on the norm: a light body (movable block,
-        // 2e-4 kg) next to a heavy one would otherwise be left with a large acceleration error.
-        if (__ballot_sync(gmask, fabsf(grad) > 2e-6f * mag + 1e-30f) == 0) break;
-        chol_rows(L, hrow, H);
-        dr = chol_solve(L, H, -grad);
-        if (me) dir[lane] = dr;
+          hrow[k] += u0 * __shfl_sync(kFull, jn, k, G) + u1 * __shfl_sync(kFull, jt1, k, G) + u2 * __shfl_sync(kFull, jt2, k, G);
+      }
+      MMZ_CONV(12);
+      const float dr = elim_solve(hrow, me ? -grad : 0.f, nv);
+      MMZ_CONV(13);
+      if (me && !done) dir[lane] = dr;
+      sync();
+      // ---- exact line search along dir: root of the monotone piecewise-linear derivative
+      float alpha = 1.f;
+      int ls = 0;
+      if (__any_sync(kFull, constrained && !done)) {
+        float dummy0 = 0.f, dummy1 = 0.f;
+        contact_products(L, cd, dr, done ? 0 : ncon, ncw, 1, &dummy0, &dummy1);
         sync();
-      } else {
-        float alpha = 1.f;
-        int ls = 0;
-        if (nrow) {
-          // exact line search along dir: root of the monotone piecewise-linear derivative
-          float md = 0.f;
-          if (me) {
-#pragma unroll 4
-            for (int k = 0; k < nv; k++) md += M[lane * L.ldm + k] * dir[k];
+        float md = 0.f;
+        if (me) {
+#pragma unroll 2
+          for (int k = 0; k < nv; k++) md += M[lane * L.ldm + k] * dir[k];
+        }
+        const float g0 = gsum<G>(me ? dr * (Ma - sm) : 0.f), h0 = gsum<G>(me ? dr * md : 0.f);
+        float lo = 0.f, hi = -1.f;
+        bool lsdone = done || !constrained;
+#pragma unroll 1
+        for (int k = 0; k < kMaxLineSearch; k++) {
+          float g = 0.f, h = 0.f;
+#pragma unroll
+          for (int s = 0; s < 2; s++) {  // this lane's limit rows: jv = +-dr
+            const float jv = s == 0 ? dr : -dr, x = ljar[s] + alpha * jv;
+            if (limD[s] > 0.f && x < 0.f) { g += limD[s] * x * jv; h += limD[s] * jv * jv; }
           }
-          const float g0 = gsum<G>(me ? dr * (Ma - sm) : 0.f, gmask), h0 = gsum<G>(me ? dr * md : 0.f, gmask);
-          float lo = 0.f, hi = -1.f;
+          if (!lsdone) {
 #pragma unroll 1
-          for (; ls < kMaxLineSearch; ls++) {
-            float g = 0.f, h = 0.f;
-#pragma unroll 1
-            for (int r = lane; r < nrow; r += G) {
-              float jar, jv, D;
-              if (r < nlim) { const float* lr = lim + r * R_STRIDE; jar = lr[R_JAR]; jv = lr[R_JV]; D = lr[R_D]; }
-              else { const float* cs = con + ((r - nlim) >> 2) * L.cstride; int e = (r - nlim) & 3; jar = cs[C_JAR + e]; jv = cs[C_JV + e]; D = cs[C_DIST]; }
-              float x = jar + alpha * jv;
+            for (int r = lane; r < 4 * ncon; r += G) {
+              const float* cs = con + (r >> 2) * L.cstride;
+              const float jv = cs[C_JV + (r & 3)], x = cs[C_JAR + (r & 3)] + alpha * jv, D = cs[C_D];
               if (x < 0.f) { g += D * x * jv; h += D * jv * jv; }
             }
-            g = gsum<G>(g, gmask) + g0 + alpha * h0;
-            h = gsum<G>(h, gmask) + h0;
-            if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) break;
-            if (g < 0.f) lo = alpha; else hi = alpha;
-            float next = alpha - g / h;
-            if (hi >= 0.f && (next <= lo || next >= hi)) next = 0.5f * (lo + hi);
-            if (next <= lo && hi < 0.f) next = 2.f * alpha + 1e-6f;
-            if (next == alpha) break;
-            alpha = next;
           }
+          g = gsum<G>(g) + g0 + alpha * h0;
+          h = gsum<G>(h) + h0;
+          if (!lsdone) {
+            if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) lsdone = true;
+            else {
+              if (g < 0.f) lo = alpha; else hi = alpha;
+              float next = alpha - g / h;
+              if (hi >= 0.f && (next <= lo || next >= hi)) next = 0.5f * (lo + hi);
+              if (next <= lo && hi < 0.f) next = 2.f * alpha + 1e-6f;
+              if (next == alpha) lsdone = true;
+              else { alpha = next; ls++; }
+            }
+          }
+          if (__all_sync(kFull, lsdone)) break;
         }
-        bool moved = false;
-        if (me) {
-          float av = a[lane], st = alpha * dr;
-          a[lane] = av + st;
-          moved = fabsf(st) > 2e-6f * fabsf(av) + 1e-6f;
-        }
-        if (lane == 0) { cn[N_ITER] = it + 1; cn[N_ITER_SUM] += 1; cn[N_LS_SUM] += ls; if (it == kMaxNewton - 1) cn[N_CAPPED] += 1; }
-        sync();
-        // unconstrained: one Newton step on the quadratic is exact. Otherwise stop at the fp32 floor,
-        // when the step no longer changes any component of the iterate.
-        stop = nrow == 0 || __ballot_sync(gmask, moved) == 0;
       }
+      bool moved = false;
+      if (me && !done) {
+        const float st = alpha * dr;
+        moved = fabsf(st) > 2e-6f * fabsf(al) + 1e-6f;
+        al += st;
+        a[lane] = al;
+      }
+      if (lane == 0 && !done) { cn[N_ITER] = it + 1; cn[N_ITER_SUM] += 1; cn[N_LS_SUM] += ls; if (it == kMaxNewton - 1) cn[N_CAPPED] += 1; }
+      sync();
+      // unconstrained: one Newton step on the quadratic is exact. Otherwise stop at the fp32 floor,
+      // when the step no longer changes any component of the iterate.
+      const unsigned movedbits = gballot(moved);
+      if (!constrained || movedbits == 0) done = true;
+      if (__all_sync(kFull, done)) break;
     }
     sync();
   }
 
   // ---------------------------------------------------------------- mj_forward
   MMZ_DI void forward(const Layout& L, bool warmstart) {
+    MMZ_CONV(1);
     kinematics(L);
+    MMZ_CONV(2);
     motion_axes(L);
     mass_matrix(L);
+    MMZ_CONV(3);
     collision(L);
+    MMZ_CONV(4);
     bias_forces(L);
     smooth_forces(L);
+    MMZ_CONV(5);
     make_constraints(L);
+    MMZ_CONV(6);
     solve(L, warmstart);
+    MMZ_CONV(7);
   }
 
   MMZ_DI bool state_bad(const Layout& L) const {
     bool bad = false;
     for (int i = lane; i < L.nq; i += G) bad |= !(fabsf(w[L.o_qpos + i]) < kMaxVal);
     for (int i = lane; i < L.nv; i += G) bad |= !(fabsf(w[L.o_qvel + i]) < kMaxVal);
-    return __ballot_sync(gmask, bad) != 0;
+    return gballot(bad) != 0;
   }
 
   // ---------------------------------------------------------------- mj_step, RK4 (mj_RungeKutta)
   // Classic tableau; stages 2-4 re-run the whole forward at x0 + h * A * k. Positions integrate on
   // the configuration manifold (mj_integratePos). Returns true if the state blew up (MuJoCo would
   // auto-reset). One forward() call site: pass i = 0..3 evaluates stage i, pass 4 only combines.
-  MMZ_DI bool mj_step(const Layout& L) {
+  MMZ_DI bool mj_step(const Layout& L, bool dead) {
     const float h = m->timestep;
     const int nq = L.nq, nv = L.nv;
     float *qpos = w + L.o_qpos, *qvel = w + L.o_qvel, *qacc = w + L.o_qacc;
     float *q0 = w + L.o_q0, *v0 = w + L.o_v0, *xv = w + L.o_xv, *fa = w + L.o_fa, *accv = w + L.o_accv, *acca = w + L.o_acca;
-    if (state_bad(L)) return true;
+    // An environment whose state is not finite is parked at qpos0 with zero velocity and keeps
+    // executing (its results are discarded by the caller): every warp-level primitive below needs
+    // all environments of the warp to run the same control flow.
+    const bool startbad = state_bad(L);
+    bool bad = dead || startbad;
+    if (bad) park(L);
+    sync();
     for (int i = lane; i < nq; i += G) q0[i] = qpos[i];
     for (int d = lane; d < nv; d += G) { v0[d] = qvel[d]; accv[d] = 0.f; acca[d] = 0.f; }
     sync();
-    bool bad = false;
 #pragma unroll 1
     for (int i = 0; i < 5; i++) {
       if (i > 0) {
@@ -1098,14 +1146,22 @@ struct Env {
       for (int d = lane; d < nv; d += G) {
         float v = qvel[d], f = qacc[d];
         badacc |= !(fabsf(f) < kMaxVal);
+        if (badacc) f = 0.f;
         xv[d] = v; fa[d] = f;
         accv[d] += B * v; acca[d] += B * f;
       }
+      if (gballot(badacc)) bad = true;  // keeps integrating (finite garbage), discarded by the caller
       sync();
-      if (i == 0 && __ballot_sync(gmask, badacc)) { bad = true; break; }
     }
     // derived arrays (xpos, contacts) deliberately stay at the 4th-stage state: SURVEY quirk Q15
-    return bad || state_bad(L);
+    const bool endbad = state_bad(L);
+    return bad || endbad;
+  }
+
+  // qpos0, zero velocity and acceleration (keeps a blown-up environment finite); the caller syncs
+  MMZ_DI void park(const Layout& L) {
+    for (int i = lane; i < L.nq; i += G) w[L.o_qpos + i] = m->qpos0[i];
+    for (int d = lane; d < L.nv; d += G) { w[L.o_qvel + d] = 0.f; w[L.o_qacc + d] = 0.f; }
   }
 };
 

@@ -53,10 +53,10 @@ MMZ_DI int row_offset(const Layout& L, int r) {
   return L.o_objpos + (r - L.nv);
 }
 
-template <int G, int NVP>
-struct Task : Env<G, NVP> {
-  using E = Env<G, NVP>;
-  using E::dv; using E::gmask; using E::lane; using E::m; using E::sync; using E::w;
+template <int G, int NVP, int FEAT>
+struct Task : Env<G, NVP, FEAT> {
+  using E = Env<G, NVP, FEAT>;
+  using E::dv; using E::lane; using E::m; using E::sync; using E::w;
 
   // CollisionDetector.detect (maze_env_utils.py:186-206); every lane computes the same result
   MMZ_DI bool seg_detect(const float* o, const float* n, float* point, float* refl) const {
@@ -117,29 +117,33 @@ struct Task : Env<G, NVP> {
     *term = t;
   }
 
-  // observed bodies: the reference reads data.xpos, which is only as fresh as the last kinematics pass
-  MMZ_DI void latch_objpos(const Layout& L) {
-    for (int i = lane; i < 3 * L.nobj; i += G) w[L.o_objpos + i] = w[L.o_xpos + 3 * m->obj_body[i / 3] + i % 3];
+  // observed bodies: the reference reads data.xpos, which is only as fresh as the last kinematics pass.
+  // `on` selects the environments that latch (warp-uniform call, predicated stores).
+  MMZ_DI void latch_objpos(const Layout& L, bool on) {
+    if (on)
+      for (int i = lane; i < 3 * L.nobj; i += G) w[L.o_objpos + i] = w[L.o_xpos + 3 * m->obj_body[i / 3] + i % 3];
     sync();
   }
   // MazeEnv._get_obs (maze_env.py:351-369) written straight to global memory, env-major
-  MMZ_DI void write_obs(const Layout& L, float* obs_g, float* obs_s, int t) {
+  MMZ_DI void write_obs(const Layout& L, float* obs_g, float* obs_s, int t, bool on) {
     const int naq = m->n_agent_q, nav = m->n_agent_v, no = 3 * L.nobj;
-    for (int i = lane; i < L.obs_dim; i += G) {
-      float v;
-      if (i < 3 && i < naq) v = w[L.o_qpos + i];
-      else if (i < 3 + no) v = w[L.o_objpos + i - 3];
-      else if (i < naq + no) v = w[L.o_qpos + i - no];
-      else if (i < naq + no + nav) v = w[L.o_qvel + i - naq - no];
-      else v = t * 0.001f;
-      obs_s[i] = v;
-      if (obs_g) obs_g[i] = v;
+    if (on) {
+      for (int i = lane; i < L.obs_dim; i += G) {
+        float v;
+        if (i < 3 && i < naq) v = w[L.o_qpos + i];
+        else if (i < 3 + no) v = w[L.o_objpos + i - 3];
+        else if (i < naq + no) v = w[L.o_qpos + i - no];
+        else if (i < naq + no + nav) v = w[L.o_qvel + i - naq - no];
+        else v = t * 0.001f;
+        obs_s[i] = v;
+        if (obs_g) obs_g[i] = v;
+      }
     }
     sync();
   }
 
   // reset_model (point.py:71-81, ant.py:84-96, swimmer.py:55-68): same distributions, Philox stream.
-  // Only writes qpos / qvel / qacc; the caller refreshes the derived arrays (finish()).
+  // Only writes qpos / qvel / qacc; the caller syncs and refreshes the derived arrays.
   MMZ_DI void reset_state(const Layout& L, unsigned long long seed, int env, int nreset, bool noise) {
     const float amp = m->reset_noise;
 #pragma unroll 1
@@ -158,15 +162,16 @@ struct Task : Env<G, NVP> {
       if (isq) w[L.o_qpos + k] = val;
       else { w[L.o_qvel + k] = val; w[L.o_qacc + k] = 0.f; }
     }
-    sync();
   }
 
   // MazeEnv.step for this environment (maze_env.py:448-481). Returns the done bits.
+  // Control flow is warp-uniform (mmz_dyn.cuh): per-environment decisions are predicates.
   // Tail passes (one kinematics / observation call site): pass 0 closes the step itself (clamp or
-  // blow-up refresh, obs, reward, done); pass 1 runs only when the episode ended and auto-reset is
-  // on, and re-observes the fresh episode.
+  // blow-up refresh, obs, reward, done); pass 1 runs only when some environment of the warp ended
+  // its episode with auto-reset on, and re-observes the fresh episode of those environments.
+  // `real` is false for the padding environments of the last warp: they compute, but write nothing.
   MMZ_DI unsigned step(const Layout& L, const float* action, float* obs_g, float* obs_s, float* reward, float* info4,
-                       int* t_io, int* nreset_io, bool auto_reset, unsigned long long seed, int genv) {
+                       int* t_io, int* nreset_io, bool auto_reset, unsigned long long seed, int genv, bool real) {
     float* qpos = w + L.o_qpos;
     float* qvel = w + L.o_qvel;
     const bool teleport = m->step_kind == MMZ_STEP_TELEPORT;
@@ -174,57 +179,61 @@ struct Task : Env<G, NVP> {
     float inner = 0.f, fwd = 0.f, cc = 0.f;
     int t = *t_io + 1;
     const float before[2] = {qpos[0], qpos[1]};
+    float act[MMZ_MAXACT];
+#pragma unroll
+    for (int a = 0; a < MMZ_MAXACT; a++) act[a] = (real && a < L.nu) ? action[a] : 0.f;
     sync();
     if (teleport) {  // PointEnv.step (point.py:44-61): turn, move, clip qvel; the motors are never driven
       if (lane == 0) {
-        float ori = qpos[2] + action[1];
+        float ori = qpos[2] + act[1];
         if (ori < -kPi) ori += 2.f * kPi;
         else if (kPi < ori) ori -= 2.f * kPi;
         float sn, cs;
         sincosf(ori, &sn, &cs);
         qpos[2] = ori;
-        qpos[0] += cs * action[0];
-        qpos[1] += sn * action[0];
+        qpos[0] += cs * act[0];
+        qpos[1] += sn * act[0];
       }
       for (int d = lane; d < L.nv; d += G) qvel[d] = fminf(fmaxf(qvel[d], -m->vel_limit), m->vel_limit);
     }
-    for (int a = lane; a < L.nu; a += G) w[L.o_ctrl + a] = teleport ? 0.f : action[a];
+#pragma unroll
+    for (int a = 0; a < MMZ_MAXACT; a++)
+      if (a < L.nu && lane == (a % G)) w[L.o_ctrl + a] = teleport ? 0.f : act[a];
     sync();
 #pragma unroll 1
-    for (int k = 0; k < m->frame_skip && !bad; k++) bad = E::mj_step(L);
+    for (int k = 0; k < m->frame_skip; k++) bad = E::mj_step(L, bad);
     bool refresh = bad;
-    if (!bad) {
-      if (teleport) {
-        if (m->manual_collision) {  // maze_env.py:450-464
-          float nw[2] = {qpos[0], qpos[1]}, pos[2];
-          sync();
-          if (clamp_move(before, nw, pos)) {
-            if (lane == 0) { qpos[0] = pos[0]; qpos[1] = pos[1]; }
-            refresh = true;  // set_xy -> set_state -> mj_forward refreshes xpos
-          }
+    if (teleport) {
+      if (m->manual_collision) {  // maze_env.py:450-464
+        float nw[2] = {qpos[0], qpos[1]}, pos[2];
+        sync();
+        if (clamp_move(before, nw, pos) && !bad) {
+          if (lane == 0) { qpos[0] = pos[0]; qpos[1] = pos[1]; }
+          refresh = true;  // set_xy -> set_state -> mj_forward refreshes xpos
         }
-      } else {  // AntEnv.step / SwimmerEnv.step (ant.py:61-73, swimmer.py:37-47)
-        float dt = m->timestep * m->frame_skip;
-        float vx = (qpos[0] - before[0]) / dt, vy = (qpos[1] - before[1]) / dt;
-        fwd = sqrtf(vx * vx + vy * vy);
-        for (int a = 0; a < L.nu; a++) cc += action[a] * action[a];
-        cc *= m->ctrl_cost_weight;
-        inner = m->forward_reward_weight * fwd - cc;
       }
+    } else if (!bad) {  // AntEnv.step / SwimmerEnv.step (ant.py:61-73, swimmer.py:37-47)
+      float dt = m->timestep * m->frame_skip;
+      float vx = (qpos[0] - before[0]) / dt, vy = (qpos[1] - before[1]) / dt;
+      fwd = sqrtf(vx * vx + vy * vy);
+#pragma unroll
+      for (int a = 0; a < MMZ_MAXACT; a++) cc += act[a] * act[a];
+      cc *= m->ctrl_cost_weight;
+      inner = m->forward_reward_weight * fwd - cc;
     }
     unsigned bits = 0;
-    if (bad) {  // MuJoCo's mj_checkPos/Vel/Acc auto-reset: back to qpos0, zero velocity
-      bits |= UNSTABLE_BIT;
-      inner = fwd = cc = 0.f;
-    }
-    bool reset_now = bad, noise = false;
+    if (bad) bits |= UNSTABLE_BIT;  // MuJoCo's mj_checkPos/Vel/Acc auto-reset: back to qpos0, zero velocity
+    bool reset_now = bad, noise = false, live = true;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
-      if (reset_now) reset_state(L, seed, genv, *nreset_io, noise);
+      if (live && reset_now) reset_state(L, seed, genv, *nreset_io, noise);
       sync();
-      if (refresh) E::kinematics(L);
-      latch_objpos(L);
-      write_obs(L, (pass == 1 || !auto_reset) ? obs_g : nullptr, obs_s, t);
+      latch_objpos(L, live && !refresh);  // stale derived arrays are the reference's behaviour (quirk Q15)
+      if (__any_sync(kFull, live && refresh)) {
+        E::kinematics(L);
+        latch_objpos(L, live && refresh);
+      }
+      write_obs(L, (real && live && (pass == 1 || !auto_reset)) ? obs_g : nullptr, obs_s, t, live);
       if (pass == 0) {
         float outer;
         bool term;
@@ -233,16 +242,16 @@ struct Task : Env<G, NVP> {
         if (term) bits |= DONE_BIT;
         if (m->max_episode_steps > 0 && t >= m->max_episode_steps) bits |= DONE_BIT | TRUNC_BIT;
         info4[0] = qpos[0]; info4[1] = qpos[1]; info4[2] = fwd; info4[3] = -cc;
-        if (!(auto_reset && (bits & DONE_BIT))) {
-          if (auto_reset) {  // no reset: the observation just assembled is the one to return
-            for (int i = lane; i < L.obs_dim; i += G) obs_g[i] = obs_s[i];
-          }
-          break;
+        live = auto_reset && (bits & DONE_BIT);
+        if (!live && auto_reset && real) {  // no reset: the observation just assembled is the one to return
+          for (int i = lane; i < L.obs_dim; i += G) obs_g[i] = obs_s[i];
         }
-        // the env that just ended starts its next episode inside this launch
-        *nreset_io += 1;
-        t = 0;
-        reset_now = true; noise = true; refresh = true;
+        if (live) {  // the env that just ended starts its next episode inside this launch
+          *nreset_io += 1;
+          t = 0;
+          reset_now = true; noise = true; refresh = true;
+        }
+        if (!__any_sync(kFull, live)) break;
       }
     }
     *t_io = t;
@@ -272,8 +281,13 @@ struct Task : Env<G, NVP> {
   }
 };
 
-template <int G, int NVP, int MODE>
-__global__ void maze_kernel(const __grid_constant__ KArgs A) {
+// register budget: enough resident groups per SM to hide the latency of the long dependent chains
+template <int G> struct LaunchCfg { static constexpr int kMaxThreads = 256, kMinBlocks = 2; };
+template <> struct LaunchCfg<32> { static constexpr int kMaxThreads = 256, kMinBlocks = 1; };
+
+template <int G, int NVP, int FEAT, int MODE>
+__global__ void __launch_bounds__(LaunchCfg<G>::kMaxThreads, LaunchCfg<G>::kMinBlocks)
+maze_kernel(const __grid_constant__ KArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;
   const Layout& L = A.L;
@@ -294,7 +308,7 @@ __global__ void maze_kernel(const __grid_constant__ KArgs A) {
   if (MODE != MODE_RESET || A.mask != nullptr) {
     for (int idx = tid; idx < L.nstate * epb; idx += blockDim.x) {
       int r = idx / epb, e = idx - r * epb;
-      if (env0 + e < A.n) wsbase[e * L.stride + row_offset(L, r)] = A.state[(size_t)r * A.npad + env0 + e];
+      if (env0 + e < A.npad) wsbase[e * L.stride + row_offset(L, r)] = A.state[(size_t)r * A.npad + env0 + e];
     }
   }
   __syncthreads();  // barrier initialised + state tile visible
@@ -307,17 +321,21 @@ __global__ void maze_kernel(const __grid_constant__ KArgs A) {
     }
   }
 
-  Task<G, NVP> T;
+  Task<G, NVP, FEAT> T;
   T.m = reinterpret_cast<const mmz_model*>(smem);
   T.dv = reinterpret_cast<const Derived*>(smem + ((sizeof(mmz_model) + 15) & ~15));
   const int ge = tid / G;  // group (environment) inside the block
   T.lane = tid % G;
-  T.gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid % 32) / G * G));
+  T.gshift = (tid % 32) / G * G;
   T.w = wsbase + ge * L.stride;
   const int env = env0 + ge;
   float* obs_s = T.w + L.o_obs;
+  // npad is a multiple of 32 and a warp's first environment a multiple of 32/G: a warp is either
+  // entirely inside [0, npad) or entirely outside, so this branch is warp-uniform. Environments in
+  // [n, npad) are padding: they run like real ones (uniform control flow) and write no outputs.
+  const bool real = env < A.n;
 
-  if (env < A.n) {
+  if (env < A.npad) {
     int t = A.counters[env], nreset = A.counters[A.npad + env];
     if (MODE == MODE_STEP) {
       float reward, info4[4];
@@ -325,64 +343,65 @@ __global__ void maze_kernel(const __grid_constant__ KArgs A) {
       T.sync();
       const float* act = A.action + (size_t)env * L.nu;
       unsigned bits = T.step(L, act, A.obs + (size_t)env * L.obs_dim, obs_s, &reward, info4, &t, &nreset,
-                             (A.flags & FLAG_AUTO_RESET) != 0, A.seed, A.env_offset + env);
+                             (A.flags & FLAG_AUTO_RESET) != 0, A.seed, A.env_offset + env, real);
       if (T.lane == 0) {
-        A.reward[env] = reward;
-        A.done[env] = (uint8_t)bits;
+        if (real) { A.reward[env] = reward; A.done[env] = (uint8_t)bits; }
         A.counters[env] = t;
         A.counters[A.npad + env] = nreset;
       }
-      if (A.info && T.lane < 4) A.info[(size_t)env * 4 + T.lane] = info4[T.lane];
-      if (A.diag && T.lane < 4) A.diag[(size_t)env * 4 + T.lane] = T.cnt(L)[N_ITER_SUM + T.lane];
+      if (real && A.info && T.lane < 4) A.info[(size_t)env * 4 + T.lane] = info4[T.lane];
+      if (real && A.diag && T.lane < 4) A.diag[(size_t)env * 4 + T.lane] = T.cnt(L)[N_ITER_SUM + T.lane];
     } else if (MODE == MODE_FORWARD) {
       for (int a = T.lane; a < L.nu; a += G)
-        T.w[L.o_ctrl + a] = T.m->step_kind == MMZ_STEP_TELEPORT ? 0.f : A.action[(size_t)env * L.nu + a];
+        T.w[L.o_ctrl + a] = (T.m->step_kind == MMZ_STEP_TELEPORT || !real) ? 0.f : A.action[(size_t)env * L.nu + a];
       T.sync();
       T.forward(L, false);
-      for (int d = T.lane; d < L.nv; d += G) A.qacc_out[(size_t)env * L.nv + d] = T.w[L.o_qacc + d];
-      if (A.diag && T.lane == 0) {
-        int* cn = T.cnt(L);
-        A.diag[env * 4 + 0] = cn[N_CON];
-        A.diag[env * 4 + 1] = cn[N_LIM] + 4 * cn[N_CON];
-        A.diag[env * 4 + 2] = cn[N_ITER];
-        A.diag[env * 4 + 3] = cn[N_OVERFLOW];
+      if (real) {
+        for (int d = T.lane; d < L.nv; d += G) A.qacc_out[(size_t)env * L.nv + d] = T.w[L.o_qacc + d];
+        if (A.diag && T.lane == 0) {
+          int* cn = T.cnt(L);
+          A.diag[env * 4 + 0] = cn[N_CON];
+          A.diag[env * 4 + 1] = cn[N_LIM] + 4 * cn[N_CON];
+          A.diag[env * 4 + 2] = cn[N_ITER];
+          A.diag[env * 4 + 3] = cn[N_OVERFLOW];
+        }
       }
     } else if (MODE == MODE_OBSERVE) {
-      T.write_obs(L, A.obs + (size_t)env * L.obs_dim, obs_s, t);
+      T.write_obs(L, real ? A.obs + (size_t)env * L.obs_dim : nullptr, obs_s, t, true);
     } else if (MODE == MODE_RESET) {
-      if (A.mask == nullptr || A.mask[env]) {
+      const bool on = A.mask == nullptr || (real && A.mask[env]);
+      if (on) {
         nreset += 1;
         t = 0;
         T.reset_state(L, A.seed, A.env_offset + env, nreset, true);
-        T.kinematics(L);
-        T.latch_objpos(L);
-        if (T.lane == 0) { A.counters[env] = 0; A.counters[A.npad + env] = nreset; }
-        if (A.obs) T.write_obs(L, A.obs + (size_t)env * L.obs_dim, obs_s, 0);
       }
+      T.sync();
+      // environments that are not reset keep their (possibly stale) derived arrays: they latched
+      // their observed-body positions when those were computed, and the tile store writes them back
+      T.kinematics(L);
+      T.latch_objpos(L, on);
+      if (on && T.lane == 0) { A.counters[env] = 0; A.counters[A.npad + env] = nreset; }
+      T.write_obs(L, (real && on && A.obs) ? A.obs + (size_t)env * L.obs_dim : nullptr, obs_s, 0, on);
     } else if (MODE == MODE_REFRESH) {  // after set_state: mj_forward refreshes the derived arrays
       for (int d = T.lane; d < L.nv; d += G) T.w[L.o_qacc + d] = 0.f;
       T.sync();
       T.kinematics(L);
-      T.latch_objpos(L);
+      T.latch_objpos(L, true);
     }
   }
   __syncthreads();
   if (MODE == MODE_STEP || MODE == MODE_RESET || MODE == MODE_REFRESH) {
     for (int idx = tid; idx < L.nstate * epb; idx += blockDim.x) {
       int r = idx / epb, e = idx - r * epb;
-      if (env0 + e < A.n) A.state[(size_t)r * A.npad + env0 + e] = wsbase[e * L.stride + row_offset(L, r)];
+      if (env0 + e < A.npad) A.state[(size_t)r * A.npad + env0 + e] = wsbase[e * L.stride + row_offset(L, r)];
     }
   }
 }
 
 typedef void (*kernel_fn)(const KArgs);
-// one translation unit per (G, NVP) instance (mmz_inst.cu, compiled in parallel)
-template <int G, int NVP>
-kernel_fn get_kernel(int mode);
-template <> kernel_fn get_kernel<8, 4>(int mode);
-template <> kernel_fn get_kernel<8, 8>(int mode);
-template <> kernel_fn get_kernel<16, 16>(int mode);
-template <> kernel_fn get_kernel<32, 20>(int mode);
+// one translation unit per (G, NVP, FEAT) instance (mmz_inst.cu, compiled in parallel); returns
+// nullptr for an instance that is not built (the caller falls back to FEAT_ALL)
+kernel_fn get_kernel(int g, int nvp, int feat, int mode);
 
 #ifdef MMZ_API_TU
 // [n][k] env-major <-> [k][npad] rows (get_state / set_state)

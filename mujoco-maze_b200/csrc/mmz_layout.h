@@ -17,25 +17,29 @@
 
 namespace mmz {
 
-// per-contact block: scalars then the 3 x nv contact-frame Jacobian (normal, tangent1, tangent2)
+// per-contact block (floats). The contact Jacobian is never stored: in the solver lane d re-derives
+// its own column (J_n, J_t1, J_t2)[d] from the contact point, frame and its motion axis cdof[d].
+// Slots 16..25 hold the narrow-phase parameters until make_constraints turns them into the row data.
 enum {
-  C_DIST = 0,   // narrow phase: dist | after row build: D (shared by the 4 pyramid edges)
-  C_POS = 1,    // narrow phase: pos[3], frame[9] | after row build: aref[4] (1..4), jar[4] (5..8), jv[4] (9..12)
-  C_FRAME = 4,
-  C_AREF = 1,
-  C_JAR = 5,
-  C_JV = 9,
-  C_BODY1 = 13,
-  C_BODY2 = 14,
-  C_MU = 15,
-  C_MARGIN = 16,
-  C_SOLREF = 17,
-  C_SOLIMP = 19,
-  C_INVW = 24,
-  C_J = 25,
+  C_POS = 0,     // [3] contact point (world; relative to the origin of body 0 after make_constraints)
+  C_FRAME = 3,   // [9] rows: normal, tangent1, tangent2
+  C_BODY1 = 12,  // body ids (-1 world) | after make_constraints: dof masks with sign +1 / -1
+  C_BODY2 = 13,
+  C_MPOS = 12,
+  C_MNEG = 13,
+  C_MU = 14,
+  C_D = 15,      // D shared by the 4 pyramid edges (after make_constraints)
+  C_AREF = 16,   // [4]
+  C_JAR = 20,    // [4] J a - aref per edge
+  C_JV = 24,     // [4] J dir per edge
+  // narrow-phase temporaries (dead once the rows are built)
+  C_DIST = 16,
+  C_MARGIN = 17,
+  C_SOLREF = 18,  // [2]
+  C_SOLIMP = 20,  // [5]
+  C_INVW = 25,
+  C_STRIDE = 29,  // odd
 };
-// per joint-limit row
-enum { R_DOF = 0, R_SIGN = 1, R_D = 2, R_AREF = 3, R_JAR = 4, R_JV = 5, R_STRIDE = 7 };
 // per-env integer counters (stored in the float workspace)
 enum { N_CON = 0, N_LIM = 1, N_ITER = 2, N_OVERFLOW = 3,
        N_ITER_SUM = 4, N_LS_SUM = 5, N_CON_MAX = 6, N_CAPPED = 7, N_CNT = 8 };  // 4..7: accumulated over one env-step
@@ -54,7 +58,6 @@ struct Layout {
   int nb, nj, nv, nq, nu, ng, nobj, obs_dim;
   int ldm;      // row stride of M and H (odd)
   int maxcon;   // contact capacity per environment
-  int maxlim;   // joint-limit row capacity
   int cstride;  // floats per contact block (odd)
   int nstate;   // persisted float rows
   int stride;   // floats per environment (stride % 32 == G % 32: groups of a warp hit distinct banks)
@@ -62,8 +65,8 @@ struct Layout {
   int o_qpos, o_qvel, o_ctrl, o_q0, o_v0, o_xv, o_fa, o_accv, o_acca;
   int o_xpos, o_xquat, o_xmat, o_xipos, o_ximat, o_xanchor, o_xaxis, o_gpos, o_gmat, o_cdof;
   int o_iw, o_ic, o_vel, o_acc, o_frc, o_fsub;
-  int o_M, o_H, o_bias, o_passive, o_smooth, o_qacc_smooth, o_qacc, o_grad, o_dir, o_tmp, o_col;
-  int o_con, o_lim, o_cnt, o_objpos, o_obs;
+  int o_M, o_smooth, o_qacc, o_dir;
+  int o_con, o_cnt, o_objpos, o_obs;
 };
 
 }  // namespace mmz

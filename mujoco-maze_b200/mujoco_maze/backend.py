@@ -13,7 +13,8 @@ from typing import Optional, Tuple
 import numpy as np
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "libmmz.so")
+# MMZ_LIB selects another build of the same library (e.g. the libmmz_dbg.so of tools/build_debug.py)
+LIB_PATH = os.path.join(_PKG_ROOT, os.environ.get("MMZ_LIB", "libmmz.so"))
 
 MMZ_DONE, MMZ_TRUNCATED, MMZ_UNSTABLE = 1, 2, 4
 MMZ_AUTO_RESET = 1

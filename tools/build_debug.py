@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Builds mujoco-maze_b200/libmmz_dbg.so with -DMMZ_DEBUG_UNIFORM (prints where a warp's control flow diverged).
+Use: MMZ_LIB=libmmz_dbg.so python tools/probe_rollout.py ... (development aid)."""
+import concurrent.futures as cf
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "mujoco-maze_b200")
+sys.path.insert(0, PKG)
+from build_native import INSTANCES  # noqa: E402
+
+flags = "-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DMMZ_DEBUG_UNIFORM".split()
+jobs = [(os.path.join(PKG, "csrc/mmz_api.cu"), "/tmp/dbg_api.o", [])]
+for g, n, f in INSTANCES:
+    jobs.append((os.path.join(PKG, "csrc/mmz_inst.cu"), f"/tmp/dbg_{g}_{n}_{f}.o", [f"-DMMZ_G={g}", f"-DMMZ_NVP={n}", f"-DMMZ_FEAT={f}"]))
+
+
+def run(j):
+    subprocess.check_call(["nvcc", *flags, *j[2], "-c", j[0], "-o", j[1]])
+    return j[1]
+
+
+with cf.ThreadPoolExecutor(8) as ex:
+    objs = list(ex.map(run, jobs))
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", os.path.join(PKG, "libmmz_dbg.so"), *objs])
+print("ok")
