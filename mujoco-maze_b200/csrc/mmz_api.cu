@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -191,8 +192,11 @@ int configure(mmz_env* h, int G, int NVP) {
     if (!h->fn[mode]) return fail(MMZ_ERR_CAPACITY, "no kernel instance for G=%d NVP=%d", G, NVP);
   }
   // block size: any whole number of warps up to the launch bound; keep the one with most resident envs
-  for (int tpb = 256; tpb >= 32; tpb -= 32) {
-    if (tpb < G) continue;
+  const int max_tpb = G == 32 ? 256 : 512;  // the kernels' launch bounds (mmz_kernels.cuh: LaunchCfg)
+  int force_tpb = 0;                        // development aid: MMZ_TPB pins the block size
+  if (const char* e = getenv("MMZ_TPB")) force_tpb = atoi(e);
+  for (int tpb = max_tpb; tpb >= 32; tpb -= 32) {
+    if (tpb < G || (force_tpb && tpb != force_tpb)) continue;
     int smem = model_smem + (tpb / G) * h->L.stride * 4;
     if (smem > dev_smem) continue;
     for (int mode = 0; mode < 5; mode++)
@@ -230,7 +234,6 @@ int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, u
   if (rc != MMZ_OK) { delete h; return rc; }
   h->device = device;
   h->n = num_envs;
-  h->npad = round_up(num_envs, 32);
   h->flags = flags;
   auto bail = [&](int code) { mmz_destroy(h); return code; };
   if (cudaSetDevice(device) != cudaSuccess) return bail(fail(MMZ_ERR_CUDA, "cudaSetDevice(%d) failed", device));
@@ -240,6 +243,14 @@ int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, u
   else if (nv <= 16) rc = configure(h, 16, 16);
   else rc = configure(h, 32, 20);
   if (rc != MMZ_OK) return bail(rc);
+  {
+    // whole blocks and whole warps only: padding environments run like real ones (uniform control
+    // flow, block-wide barriers inside the step) and write no outputs
+    const int epb = h->tpb / h->G;
+    int unit = epb;
+    while (unit % 32) unit += epb;  // lcm(epb, 32)
+    h->npad = round_up(num_envs, unit);
+  }
   // device copy of the constants: model + derived tables, padded to a multiple of 16 bytes
   {
     unsigned char* host = new (std::nothrow) unsigned char[h->L.model_bytes];

@@ -1063,6 +1063,11 @@ struct Env {
 
   // ---------------------------------------------------------------- mj_forward
   MMZ_DI void forward(const Layout& L, bool warmstart) {
+    // Every warp of the block starts each forward evaluation together: the step is instruction-fetch
+    // bound (a ~100 KB loop body against a much smaller instruction cache), and warps that walk the
+    // same code at the same time share the fetched lines. All blocks are full (npad is a multiple of
+    // the block's environment count) and every warp runs the same number of evaluations.
+    __syncthreads();
     MMZ_CONV(1);
     kinematics(L);
     MMZ_CONV(2);

@@ -282,7 +282,7 @@ struct Task : Env<G, NVP, FEAT> {
 };
 
 // register budget: enough resident groups per SM to hide the latency of the long dependent chains
-template <int G> struct LaunchCfg { static constexpr int kMaxThreads = 256, kMinBlocks = 2; };
+template <int G> struct LaunchCfg { static constexpr int kMaxThreads = 512, kMinBlocks = 1; };  // <= 128 registers
 template <> struct LaunchCfg<32> { static constexpr int kMaxThreads = 256, kMinBlocks = 1; };
 
 template <int G, int NVP, int FEAT, int MODE>
