@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libmmz.so")
 # (lanes per env, padded nv, FEAT bits: 1 box geoms, 2 fluid) - keep in step with MMZ_INSTANCES in csrc/mmz_api.cu
-INSTANCES = ((8, 4, 1), (8, 4, 3), (8, 8, 2), (8, 8, 3), (16, 16, 0), (16, 16, 1), (16, 16, 3), (32, 20, 3))
+INSTANCES = ((8, 4, 1), (8, 4, 3), (8, 8, 2), (8, 8, 3), (16, 14, 0), (16, 16, 0), (16, 16, 1), (16, 16, 3), (32, 20, 3))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -39,7 +39,7 @@ typedef mmz::kernel_fn kernel_fn;
 }  // namespace
 
 // kernel instances (one translation unit each, see build_native.py INSTANCES)
-#define MMZ_INSTANCES(X) X(8, 4, 1) X(8, 4, 3) X(8, 8, 2) X(8, 8, 3) X(16, 16, 0) X(16, 16, 1) X(16, 16, 3) X(32, 20, 3)
+#define MMZ_INSTANCES(X) X(8, 4, 1) X(8, 4, 3) X(8, 8, 2) X(8, 8, 3) X(16, 14, 0) X(16, 16, 0) X(16, 16, 1) X(16, 16, 3) X(32, 20, 3)
 namespace mmz {
 #define MMZ_DECL(g, nvp, feat) kernel_fn get_kernel_##g##_##nvp##_##feat(int mode);
 MMZ_INSTANCES(MMZ_DECL)
@@ -58,6 +58,7 @@ struct mmz_env {
   unsigned flags = 0;
   int G = 32, NVP = 20;  // kernel instance
   int feat = 0;          // FEAT_* bits the instance was compiled with
+  unsigned bsync = 1;    // block-barrier placement inside the step (mmz_dyn.cuh: Env::bsync)
   int tpb = 128;         // threads per block
   int smem_bytes = 0;
   int envs_per_sm = 0;
@@ -157,7 +158,7 @@ int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s) {
   A.counters = h->d_counters;
   A.n = h->n;
   A.npad = h->npad;
-  A.flags = h->flags;
+  A.flags = h->flags | (h->bsync << 8);
   A.env_offset = h->env_offset;
   int epb = h->tpb / h->G;
   int blocks = (h->npad + epb - 1) / epb;  // padding environments run too (warp-uniform control flow)
@@ -165,6 +166,12 @@ int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s) {
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return MMZ_OK;
+}
+
+int nbox_geoms(const mmz_model& m) {
+  int n = 0;
+  for (int g = 0; g < m.ngeom; g++) n += m.geom_type[g] == MMZ_GEOM_BOX;
+  return n;
 }
 
 int configure(mmz_env* h, int G, int NVP) {
@@ -195,6 +202,7 @@ int configure(mmz_env* h, int G, int NVP) {
   const int max_tpb = G == 32 ? 256 : 512;  // the kernels' launch bounds (mmz_kernels.cuh: LaunchCfg)
   int force_tpb = 0;                        // development aid: MMZ_TPB pins the block size
   if (const char* e = getenv("MMZ_TPB")) force_tpb = atoi(e);
+  if (const char* e = getenv("MMZ_SYNC")) h->bsync = (unsigned)atoi(e) & 7u;
   for (int tpb = max_tpb; tpb >= 32; tpb -= 32) {
     if (tpb < G || (force_tpb && tpb != force_tpb)) continue;
     int smem = model_smem + (tpb / G) * h->L.stride * 4;
@@ -240,6 +248,8 @@ int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, u
   const int nv = h->hm.nv;
   if (nv <= 4 && h->hm.nbody <= 8 && h->hm.ngeom <= 8) rc = configure(h, 8, 4);
   else if (nv <= 8) rc = configure(h, 8, 8);
+  else if (nv <= 14 && nbox_geoms(h->hm) == 0 && h->hm.density <= 0.f && h->hm.viscosity <= 0.f)
+    rc = configure(h, 16, 14);  // the Ant family without movable blocks: rows of exactly 14 registers
   else if (nv <= 16) rc = configure(h, 16, 16);
   else rc = configure(h, 32, 20);
   if (rc != MMZ_OK) return bail(rc);

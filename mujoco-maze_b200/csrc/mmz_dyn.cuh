@@ -74,6 +74,7 @@ struct Env {
   float* w;            // this environment's workspace (shared memory)
   int lane;            // 0..G-1
   int gshift;          // bit position of this group's lane 0 inside the warp
+  unsigned bsync;      // block-barrier placement (bit 0: start of every forward, bit 1: before the solve, bit 2: per mj_step)
 
   MMZ_DI void sync() const { __syncwarp(); }
   // ballot restricted to this group's lanes (bit i = lane i of the group)
@@ -1067,7 +1068,7 @@ struct Env {
     // bound (a ~100 KB loop body against a much smaller instruction cache), and warps that walk the
     // same code at the same time share the fetched lines. All blocks are full (npad is a multiple of
     // the block's environment count) and every warp runs the same number of evaluations.
-    __syncthreads();
+    if (bsync & 1) __syncthreads();
     MMZ_CONV(1);
     kinematics(L);
     MMZ_CONV(2);
@@ -1080,6 +1081,7 @@ struct Env {
     smooth_forces(L);
     MMZ_CONV(5);
     make_constraints(L);
+    if (bsync & 2) __syncthreads();
     MMZ_CONV(6);
     solve(L, warmstart);
     MMZ_CONV(7);
@@ -1104,6 +1106,7 @@ struct Env {
     // An environment whose state is not finite is parked at qpos0 with zero velocity and keeps
     // executing (its results are discarded by the caller): every warp-level primitive below needs
     // all environments of the warp to run the same control flow.
+    if (bsync & 4) __syncthreads();
     const bool startbad = state_bad(L);
     bool bad = dead || startbad;
     if (bad) park(L);

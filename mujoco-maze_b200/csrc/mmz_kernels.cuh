@@ -327,6 +327,7 @@ maze_kernel(const __grid_constant__ KArgs A) {
   const int ge = tid / G;  // group (environment) inside the block
   T.lane = tid % G;
   T.gshift = (tid % 32) / G * G;
+  T.bsync = A.flags >> 8;
   T.w = wsbase + ge * L.stride;
   const int env = env0 + ge;
   float* obs_s = T.w + L.o_obs;
