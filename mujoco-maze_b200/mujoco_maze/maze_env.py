@@ -50,6 +50,7 @@ class MazeEnv(gym.Env):
         num_envs: Optional[int] = None,
         device: str = "cuda:0",
         auto_reset: bool = False,
+        env_offset: int = 0,
         seed: int = 0,
         max_episode_steps: int = 1000,
         **kwargs,
@@ -58,6 +59,7 @@ class MazeEnv(gym.Env):
         self.num_envs = int(num_envs) if self.is_batched else 1
         self.device = device
         self._auto_reset = bool(auto_reset)
+        self._env_offset = int(env_offset)  # global index of env 0 when this batch is one shard of a larger one
         self._seed = int(seed)
         self._episode = 0
 
@@ -119,7 +121,8 @@ class MazeEnv(gym.Env):
         if self._sim is None:
             from mujoco_maze.backend import BatchedSim
 
-            self._sim = BatchedSim(self.model, self.num_envs, self.device, auto_reset=self._auto_reset)
+            self._sim = BatchedSim(self.model, self.num_envs, self.device, auto_reset=self._auto_reset,
+                                   env_offset=self._env_offset)
         return self._sim
 
     def _state(self):
