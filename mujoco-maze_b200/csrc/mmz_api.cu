@@ -14,6 +14,7 @@
 #include "../../include/mmz.h"
 #define MMZ_API_TU
 #include "mmz_kernels.cuh"
+#include "mmz_hstep.cuh"
 
 using namespace mmz;
 
@@ -41,6 +42,8 @@ typedef mmz::kernel_fn kernel_fn;
 // kernel instances (one translation unit each, see build_native.py INSTANCES)
 #define MMZ_INSTANCES(X) X(8, 4, 1) X(8, 4, 3) X(8, 8, 2) X(8, 8, 3) X(16, 14, 0) X(16, 16, 0) X(16, 16, 1) X(16, 16, 3) X(32, 20, 3)
 namespace mmz {
+hkernel_fn get_hkernel_14(int mode);
+hkernel_fn get_hkernel_16(int mode);
 #define MMZ_DECL(g, nvp, feat) kernel_fn get_kernel_##g##_##nvp##_##feat(int mode);
 MMZ_INSTANCES(MMZ_DECL)
 #undef MMZ_DECL
@@ -75,6 +78,10 @@ struct mmz_env {
   unsigned long long launches = 0;
   int32_t* d_step_diag = nullptr;  // caller-owned, optional
   kernel_fn fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // hybrid kernel (mmz_hkernel.cuh), used when the model is eligible
+  bool use_t = false;
+  TLayout TL;
+  mmz::hkernel_fn tfn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -152,6 +159,20 @@ int validate(const mmz_model& m) {
 }
 
 int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s) {
+  if (h->use_t) {
+    TArgs T;
+    memset(&T, 0, sizeof T);
+    T.L = h->TL;
+    T.model = h->d_model; T.state = h->d_state; T.counters = h->d_counters;
+    T.n = h->n; T.npad = h->npad;
+    T.action = A.action; T.obs = A.obs; T.reward = A.reward; T.done = A.done; T.info = A.info;
+    T.qacc_out = A.qacc_out; T.diag = A.diag; T.mask = A.mask; T.seed = A.seed;
+    T.flags = h->flags; T.env_offset = h->env_offset;
+    h->tfn[mode]<<<h->npad / TE, TW * 32, h->smem_bytes, s>>>(T);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return MMZ_OK;
+  }
   A.L = h->L;
   A.model = h->d_model;
   A.state = h->d_state;
@@ -174,6 +195,91 @@ int nbox_geoms(const mmz_model& m) {
   return n;
 }
 
+// The hybrid kernel (mmz_hkernel.cuh) handles torque-driven agents with at most 16 dofs whose moving geoms are
+// spheres / capsules that only touch the world (floor, maze boxes): the Ant family. Returns false if the model is
+// not eligible (the lanes-per-environment kernel of mmz_dyn.cuh serves everything).
+bool configure_h(mmz_env* h, int* rc) {
+  const mmz_model& m = h->hm;
+  *rc = MMZ_OK;
+  const char* kenv = getenv("MMZ_KERNEL");  // development aid: "groups" forces the lanes-per-environment kernel
+  if (kenv && !strcmp(kenv, "groups")) return false;
+  if (m.step_kind != MMZ_STEP_TORQUE || m.manual_collision) return false;
+  if (m.density > 0.f || m.viscosity > 0.f) return false;
+  if (m.nv < 9 || m.nv > 16) return false;  // small models are already served well by 8 lanes per environment
+  for (int g = 0; g < m.ngeom; g++) {
+    if (m.geom_type[g] != MMZ_GEOM_SPHERE && m.geom_type[g] != MMZ_GEOM_CAPSULE) return false;
+    for (int g2 = g + 1; g2 < m.ngeom; g2++) {  // no moving-moving pair may pass the contact filter
+      const int b1 = m.geom_body[g], b2 = m.geom_body[g2];
+      if (b1 == b2 || m.body_parent[b1] == b2 || m.body_parent[b2] == b1) continue;
+      if ((m.geom_contype[g] & m.geom_conaffinity[g2]) || (m.geom_contype[g2] & m.geom_conaffinity[g])) return false;
+    }
+  }
+  TLayout L;
+  memset(&L, 0, sizeof L);
+  L.nb = m.nbody; L.nj = m.njnt; L.nv = m.nv; L.nq = m.nq; L.nu = m.nu; L.ng = m.ngeom; L.nobj = m.nobj; L.obs_dim = m.obs_dim;
+  int nlev = 0;
+  for (int b = 0; b < m.nbody; b++)
+    if (m.body_level[b] + 1 > nlev) nlev = m.body_level[b] + 1;
+  L.nlev = nlev; L.ldm = m.nv + 1;
+  L.cstride = C_STRIDE;
+  L.nstate = m.nq + 2 * m.nv + 3 * m.nobj;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += n; return r; };
+  L.o_cnt = take(TN_CNT);
+  L.o_qpos = take(L.nq); L.o_qvel = take(L.nv); L.o_qacc = take(L.nv); L.o_objpos = take(3 * L.nobj > 0 ? 3 * L.nobj : 1);
+  L.o_ctrl = take(L.nu > 0 ? L.nu : 1); L.o_act = take(L.nu > 0 ? L.nu : 1);
+  L.o_q0 = take(L.nq); L.o_v0 = take(L.nv); L.o_accv = take(L.nv); L.o_acca = take(L.nv);
+  L.o_xpos = take(3 * L.nb); L.o_xquat = take(4 * L.nb); L.o_xmat = take(9 * L.nb);
+  L.o_gpos = take(3 * L.ng); L.o_gax = take(3 * L.ng);
+  L.o_cdof = take(6 * L.nv);
+  L.o_iw = take(10 * L.nb); L.o_vel = take(6 * L.nb);
+  L.o_ic = take(10 * L.nb); L.o_acc = take(6 * L.nb); L.o_frc = take(6 * L.nb); L.o_fsub = take(6 * L.nb);
+  L.o_M = take(L.nv * L.ldm);
+  L.o_smooth = take(L.nv); L.o_dir = take(L.nv);
+  L.o_gcnt = take(L.ng > 0 ? L.ng : 1); L.o_obs = take(L.obs_dim);
+  L.model_bytes = round_up(round_up((int)sizeof(mmz_model), 16) + (int)sizeof(TDerived), 16);
+  int dev_smem = 0;
+  if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess) return false;
+  const int avail = (dev_smem - round_up(L.model_bytes, 128) - 256) / (HS * 4);  // slots per environment
+  int maxcon = (avail - o) / L.cstride;
+  if (maxcon > 24) maxcon = 24;
+  if (maxcon < 12) return false;  // does not fit: use the lanes-per-environment kernel
+  L.maxcon = maxcon;
+  L.o_con = take(maxcon * L.cstride);
+  L.nslots = o;
+  h->TL = L;
+  h->smem_bytes = round_up(L.model_bytes, 128) + L.nslots * HS * 4;
+  for (int mode = 0; mode < 5; mode++) {
+    h->tfn[mode] = m.nv <= 14 ? mmz::get_hkernel_14(mode) : mmz::get_hkernel_16(mode);
+    cudaError_t e = cudaFuncSetAttribute(h->tfn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
+    if (e != cudaSuccess) { *rc = fail(MMZ_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return false; }
+  }
+  h->use_t = true;
+  h->G = 16; h->NVP = m.nv <= 14 ? 14 : 16; h->tpb = TW * 32; h->envs_per_sm = TE;
+  h->L.stride = L.nslots; h->L.nstate = L.nstate; h->L.model_bytes = L.model_bytes;
+  return true;
+}
+
+void make_tderived(const mmz_model& m, TDerived* d) {
+  memset(d, 0, sizeof *d);
+  int nlev = 0;
+  for (int b = 0; b < m.nbody; b++) {
+    int mask = 0;
+    for (int a = b; a >= 0; a = m.body_parent[a]) mask |= 1 << a;
+    d->anc[b] = mask;
+    if (m.body_level[b] + 1 > nlev) nlev = m.body_level[b] + 1;
+  }
+  d->nlev = nlev;
+  int k = 0;
+  for (int l = 0; l < nlev; l++) {
+    d->lvl_off[l] = k;
+    for (int b = 0; b < m.nbody; b++)
+      if (m.body_level[b] == l) d->lvl_body[k++] = b;
+  }
+  d->lvl_off[nlev] = k;
+  d->ident[0] = d->ident[4] = d->ident[8] = 1.f;
+}
+
 int configure(mmz_env* h, int G, int NVP) {
   h->G = G;
   h->NVP = NVP;
@@ -188,6 +294,7 @@ int configure(mmz_env* h, int G, int NVP) {
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
   const int model_smem = round_up(h->L.model_bytes, 128);
   int best_tpb = 0, best_envs = 0, best_smem = 0;
+  bool best_spreads = false;
   // features this model needs; an instance compiled without the unused ones is preferred
   int feat = 0;
   if (nbox) feat |= FEAT_BOX;
@@ -212,7 +319,11 @@ int configure(mmz_env* h, int G, int NVP) {
     int nblk = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, h->fn[MODE_STEP], tpb, smem));
     int envs = nblk * (tpb / G);
-    if (envs > best_envs) { best_envs = envs; best_tpb = tpb; best_smem = smem; }
+    // a batch too small to give every SM a block of this size is better served by smaller blocks
+    const bool spreads = (long)(h->n + tpb / G - 1) / (tpb / G) >= sms || tpb <= 64;
+    if (envs > best_envs && (spreads || !best_tpb)) { best_envs = envs; best_tpb = tpb; best_smem = smem; }
+    else if (best_tpb && !best_spreads && spreads) { best_envs = envs; best_tpb = tpb; best_smem = smem; }
+    if (best_tpb == tpb) best_spreads = spreads;
   }
   if (!best_tpb) return fail(MMZ_ERR_CAPACITY, "workspace of %d bytes per environment does not fit in shared memory", h->L.stride * 4);
   h->tpb = best_tpb;
@@ -220,7 +331,6 @@ int configure(mmz_env* h, int G, int NVP) {
   h->envs_per_sm = best_envs;
   for (int mode = 0; mode < 5; mode++)
     CUDA_TRY(cudaFuncSetAttribute(h->fn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, best_smem));
-  (void)sms;
   return MMZ_OK;
 }
 
@@ -246,7 +356,9 @@ int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, u
   auto bail = [&](int code) { mmz_destroy(h); return code; };
   if (cudaSetDevice(device) != cudaSuccess) return bail(fail(MMZ_ERR_CUDA, "cudaSetDevice(%d) failed", device));
   const int nv = h->hm.nv;
-  if (nv <= 4 && h->hm.nbody <= 8 && h->hm.ngeom <= 8) rc = configure(h, 8, 4);
+  if (configure_h(h, &rc)) rc = MMZ_OK;
+  else if (rc != MMZ_OK) return bail(rc);
+  else if (nv <= 4 && h->hm.nbody <= 8 && h->hm.ngeom <= 8) rc = configure(h, 8, 4);
   else if (nv <= 8) rc = configure(h, 8, 8);
   else if (nv <= 14 && nbox_geoms(h->hm) == 0 && h->hm.density <= 0.f && h->hm.viscosity <= 0.f)
     rc = configure(h, 16, 14);  // the Ant family without movable blocks: rows of exactly 14 registers
@@ -256,7 +368,7 @@ int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, u
   {
     // whole blocks and whole warps only: padding environments run like real ones (uniform control
     // flow, block-wide barriers inside the step) and write no outputs
-    const int epb = h->tpb / h->G;
+    const int epb = h->use_t ? TE : h->tpb / h->G;
     int unit = epb;
     while (unit % 32) unit += epb;  // lcm(epb, 32)
     h->npad = round_up(num_envs, unit);
@@ -267,9 +379,15 @@ int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, u
     if (!host) return bail(fail(MMZ_ERR_INVALID, "out of host memory"));
     memset(host, 0, h->L.model_bytes);
     memcpy(host, &h->hm, sizeof(mmz_model));
-    Derived dv;
-    make_derived(h->hm, &dv);
-    memcpy(host + round_up((int)sizeof(mmz_model), 16), &dv, sizeof dv);
+    if (h->use_t) {
+      TDerived dv;
+      make_tderived(h->hm, &dv);
+      memcpy(host + round_up((int)sizeof(mmz_model), 16), &dv, sizeof dv);
+    } else {
+      Derived dv;
+      make_derived(h->hm, &dv);
+      memcpy(host + round_up((int)sizeof(mmz_model), 16), &dv, sizeof dv);
+    }
     cudaError_t e = cudaMalloc(&h->d_model, h->L.model_bytes);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_model, host, h->L.model_bytes, cudaMemcpyHostToDevice);
     delete[] host;

@@ -1,0 +1,19 @@
+// mmz_hinst.cu - hybrid kernel instances: -DMMZ_NVP=<registers per Hessian row> (14 or 16), one per mode.
+#include "mmz_hstep.cuh"
+
+#define MMZ_HCAT_(a, b) a##b
+#define MMZ_HCAT(a, b) MMZ_HCAT_(a, b)
+
+namespace mmz {
+
+hkernel_fn MMZ_HCAT(get_hkernel_, MMZ_NVP)(int mode) {
+  switch (mode) {
+    case TMODE_STEP: return maze_hkernel<MMZ_NVP, TMODE_STEP>;
+    case TMODE_FORWARD: return maze_hkernel<MMZ_NVP, TMODE_FORWARD>;
+    case TMODE_OBSERVE: return maze_hkernel<MMZ_NVP, TMODE_OBSERVE>;
+    case TMODE_RESET: return maze_hkernel<MMZ_NVP, TMODE_RESET>;
+    default: return maze_hkernel<MMZ_NVP, TMODE_REFRESH>;
+  }
+}
+
+}  // namespace mmz

@@ -1,0 +1,891 @@
+// mmz_hkernel.cuh - the hybrid step kernel for the Ant family: two thread-to-data mappings in one block.
+//
+// A block owns 32 environments (one SM: 512 threads, the whole shared memory) and switches between two
+// views of the same shared-memory workspace, separated by block barriers:
+//
+//   * TREE phases, "lane = environment" : lane e of every warp works on environment e and
+//     the warps split the bodies of a tree level / geoms / dofs / contact slots between them. Kinematics,
+//     motion axes, spatial inertias, RNE, the mass matrix, collision and the contact rows run this way:
+//     all 32 lanes do useful work (the lanes <-> bodies mapping of mmz_dyn.cuh keeps 4..13 of 32 busy),
+//     and a warp without an item costs no issue slots.
+//   * SOLVER phase, "16 lanes = one environment, lane = degree of freedom" (mmz_dyn.cuh): warp w solves
+//     environments w and w + 16. The Newton solve is register-resident (Hessian row per lane, shuffle
+//     Gaussian elimination) and its iteration count is only shared by the 2 environments of a warp, not by
+//     all 32 of the block.
+//
+// The workspace is laid out [slot][33]: element (slot, env) lives at slot * 33 + env. In the tree view
+// (fixed slot per instruction, lanes = 32 environments) the bank is (slot + env) % 32: conflict-free, also
+// for lane-varying slots. In the solver view a warp touches 16 consecutive slots for environments w and
+// w + 16: banks slot + w + {0..15} and slot + w + 16 + {0..15}: conflict-free too.
+#pragma once
+#include "mmz_layout.h"
+#include "mmz_narrow.cuh"
+
+namespace mmz {
+
+constexpr int TW = 16;  // warps per block
+constexpr int TE = 32;  // environments per block
+constexpr unsigned kAll = 0xffffffffu;
+constexpr int kTMaxNewton = 24;
+constexpr int kTMaxLineSearch = 24;
+
+enum { TMODE_STEP = 0, TMODE_FORWARD = 1, TMODE_OBSERVE = 2, TMODE_RESET = 3, TMODE_REFRESH = 4 };
+enum { T_DONE_BIT = 1, T_TRUNC_BIT = 2, T_UNSTABLE_BIT = 4 };
+enum { T_FLAG_AUTO_RESET = 1 };
+
+// per-environment integers
+enum { TN_CON = 0, TN_OVERFLOW = 1, TN_ITER = 2, TN_NOTCONV = 3, TN_ITER_SUM = 4, TN_LS_SUM = 5, TN_CON_MAX = 6,
+       TN_CAPPED = 7, TN_MOVED = 8, TN_BAD = 9, TN_LIM = 10, TN_CNT = 12 };
+
+struct TDerived {               // appended to the model blob in device memory
+  int32_t anc[MMZ_MAXBODY];     // bit a set in anc[b]: body a is b or an ancestor of b
+  int32_t lvl_off[MMZ_MAXBODY + 1];  // bodies of level l: lvl_body[lvl_off[l] .. lvl_off[l+1])
+  int32_t lvl_body[MMZ_MAXBODY];
+  int32_t nlev;
+  int32_t pad[3];
+  float ident[9];
+  float padf[3];
+};
+
+struct TLayout {
+  int nb, nj, nv, nq, nu, ng, nobj, obs_dim, nlev;
+  int maxcon, cstride, ldm, nstate, nslots, model_bytes;
+  int o_qpos, o_qvel, o_qacc, o_objpos;  // persisted rows, in this order
+  int o_ctrl, o_q0, o_v0, o_accv, o_acca;
+  int o_xpos, o_xquat, o_xmat, o_gpos, o_gax, o_cdof;
+  int o_iw, o_ic, o_vel, o_acc, o_frc, o_fsub;
+  int o_M, o_smooth, o_dir;
+  int o_con, o_cnt, o_gcnt, o_obs, o_act;
+};
+
+struct TArgs {
+  TLayout L;
+  const void* model;
+  float* state;        // [L.nstate][npad]
+  int* counters;       // [2][npad]: t, number of resets
+  int n, npad;
+  const float* action; // [n][nu]
+  float* obs;          // [n][obs_dim]
+  float* reward;       // [n]
+  uint8_t* done;       // [n]
+  float* info;         // [n][4] or null
+  float* qacc_out;     // TMODE_FORWARD: [n][nv]
+  int* diag;           // [n][4], optional
+  const uint8_t* mask; // TMODE_RESET
+  unsigned long long seed;
+  unsigned flags;
+  int env_offset;
+};
+
+
+constexpr int HS = 33;  // row stride of the [slot][33] workspace
+
+template <int NVP>
+struct HEnv {
+  const mmz_model* m;
+  const TDerived* dv;
+  float* sm;
+  int e, wid;               // tree view: lane = environment e; warp wid takes items wid, wid + 16, ...
+  int genv, lane, gshift;   // solver view: environment wid + 16 * (laneid / 16), lane = dof
+  float limD[2], limA[2];   // this lane's joint-limit rows (solver view)
+
+#define S(i) sm[(i) * HS + e]
+#define W_(i) sm[(i) * HS + genv]
+  MMZ_DI int& I(int i) const { return reinterpret_cast<int*>(sm)[i * HS + e]; }
+  MMZ_DI int& IW(int i) const { return reinterpret_cast<int*>(sm)[i * HS + genv]; }
+  // spatial quantities are taken about a point near the robot (its first three coordinates), not the world
+  // origin: translation invariant, and it avoids fp32 cancellation far from the maze origin
+  MMZ_DI void ref(const TLayout& L, float* r) const {
+    r[0] = S(L.o_qpos); r[1] = S(L.o_qpos + 1); r[2] = (m->jnt_type[0] == MMZ_JNT_FREE) ? S(L.o_qpos + 2) : 0.f;
+  }
+
+  // ------------------------------------------------------------------ phase A: one body of a tree level
+  // kinematics (mj_kinematics), its motion axes, its world spatial inertia and the forward pass of RNE
+  MMZ_DI void body_pass(const TLayout& L, int b) {
+    const int p = m->body_parent[b];
+    float pos[3], quat[4], R[9], rf[3];
+    ref(L, rf);
+    if (p < 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) pos[k] = m->body_pos[b][k];
+#pragma unroll
+      for (int k = 0; k < 4; k++) quat[k] = m->body_quat[b][k];
+    } else {
+      float Rp[9], qp[4];
+#pragma unroll
+      for (int k = 0; k < 9; k++) Rp[k] = S(L.o_xmat + 9 * p + k);
+#pragma unroll
+      for (int k = 0; k < 4; k++) qp[k] = S(L.o_xquat + 4 * p + k);
+      mat_vec(pos, Rp, m->body_pos[b]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) pos[k] += S(L.o_xpos + 3 * p + k);
+      quat_mul(quat, qp, m->body_quat[b]);
+    }
+    const int j0 = m->body_jntadr[b], j1 = j0 + m->body_jntnum[b];
+    int freed = -1;  // first dof of a free joint of this body
+#pragma unroll 1
+    for (int j = j0; j < j1; j++) {
+      const int qa = m->jnt_qadr[j], type = m->jnt_type[j], d = m->jnt_dadr[j];
+      if (type == MMZ_JNT_FREE) {
+        float q[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) q[k] = S(L.o_qpos + qa + 3 + k);
+        quat_norm(q);  // MuJoCo normalises the stored quaternion in place
+#pragma unroll
+        for (int k = 0; k < 4; k++) { S(L.o_qpos + qa + 3 + k) = q[k]; quat[k] = q[k]; }
+#pragma unroll
+        for (int k = 0; k < 3; k++) pos[k] = S(L.o_qpos + qa + k);
+        freed = d;
+        continue;
+      }
+      // hinge / slide: axis and anchor in the frame reached so far; its motion axis about the reference point
+      quat2mat(R, quat);
+      float an[3], ax[3], c[6];
+      mat_vec(an, R, m->jnt_pos[j]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) an[k] += pos[k];
+      mat_vec(ax, R, m->jnt_axis[j]);
+      const float dq = S(L.o_qpos + qa) - m->qpos0[qa];
+      if (type == MMZ_JNT_SLIDE) {
+        c[0] = c[1] = c[2] = 0.f; c[3] = ax[0]; c[4] = ax[1]; c[5] = ax[2];
+#pragma unroll
+        for (int k = 0; k < 3; k++) pos[k] += ax[k] * dq;
+      } else {  // hinge: rotate about the anchor
+        float at[3] = {an[0] - rf[0], an[1] - rf[1], an[2] - rf[2]};
+        cross3(c + 3, at, ax);
+        c[0] = ax[0]; c[1] = ax[1]; c[2] = ax[2];
+        float qr[4], q2[4], off[3];
+        axisangle2quat(qr, m->jnt_axis[j], dq);
+        quat_mul(q2, quat, qr);
+#pragma unroll
+        for (int k = 0; k < 4; k++) quat[k] = q2[k];
+        quat2mat(R, quat);
+        mat_vec(off, R, m->jnt_pos[j]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) pos[k] = an[k] - off[k];
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) S(L.o_cdof + 6 * d + i) = c[i];
+    }
+    quat_norm(quat);
+    quat2mat(R, quat);
+#pragma unroll
+    for (int k = 0; k < 3; k++) S(L.o_xpos + 3 * b + k) = pos[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) S(L.o_xquat + 4 * b + k) = quat[k];
+#pragma unroll
+    for (int k = 0; k < 9; k++) S(L.o_xmat + 9 * b + k) = R[k];
+    if (freed >= 0) {  // free joint: 3 world-aligned translations, then rotations about the body axes through its origin
+      const float at[3] = {pos[0] - rf[0], pos[1] - rf[1], pos[2] - rf[2]};
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) S(L.o_cdof + 6 * (freed + k) + i) = (i == 3 + k) ? 1.f : 0.f;
+        const float ax[3] = {R[k], R[3 + k], R[6 + k]};
+        float lin[3];
+        cross3(lin, at, ax);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { S(L.o_cdof + 6 * (freed + 3 + k) + i) = ax[i]; S(L.o_cdof + 6 * (freed + 3 + k) + 3 + i) = lin[i]; }
+      }
+    }
+    const int d0 = m->body_dofadr[b], d1 = d0 + m->body_dofnum[b];
+
+    // ---- world spatial inertia about the reference point
+    float Iw[10];
+    {
+      float ip[3], qi[4], Ri[9], c[3];
+      mat_vec(ip, R, m->body_ipos[b]);
+      quat_mul(qi, quat, m->body_iquat[b]);
+      quat2mat(Ri, qi);
+#pragma unroll
+      for (int k = 0; k < 3; k++) c[k] = ip[k] + pos[k] - rf[k];
+      const float* dg = m->body_inertia[b];
+      const float mass = m->body_mass[b], cc = dot3(c, c);
+      Iw[0] = Ri[0] * Ri[0] * dg[0] + Ri[1] * Ri[1] * dg[1] + Ri[2] * Ri[2] * dg[2] + mass * (cc - c[0] * c[0]);
+      Iw[1] = Ri[3] * Ri[3] * dg[0] + Ri[4] * Ri[4] * dg[1] + Ri[5] * Ri[5] * dg[2] + mass * (cc - c[1] * c[1]);
+      Iw[2] = Ri[6] * Ri[6] * dg[0] + Ri[7] * Ri[7] * dg[1] + Ri[8] * Ri[8] * dg[2] + mass * (cc - c[2] * c[2]);
+      Iw[3] = Ri[0] * Ri[3] * dg[0] + Ri[1] * Ri[4] * dg[1] + Ri[2] * Ri[5] * dg[2] - mass * c[0] * c[1];
+      Iw[4] = Ri[0] * Ri[6] * dg[0] + Ri[1] * Ri[7] * dg[1] + Ri[2] * Ri[8] * dg[2] - mass * c[0] * c[2];
+      Iw[5] = Ri[3] * Ri[6] * dg[0] + Ri[4] * Ri[7] * dg[1] + Ri[5] * Ri[8] * dg[2] - mass * c[1] * c[2];
+      Iw[6] = mass * c[0]; Iw[7] = mass * c[1]; Iw[8] = mass * c[2];
+      Iw[9] = mass;
+#pragma unroll
+      for (int k = 0; k < 10; k++) S(L.o_iw + 10 * b + k) = Iw[k];
+    }
+
+    // ---- RNE forward: velocity and bias acceleration of the body, then its inertial force
+    float v[6], a[6];
+    if (p < 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) { v[k] = 0.f; a[k] = 0.f; }
+#pragma unroll
+      for (int k = 0; k < 3; k++) a[3 + k] = -m->gravity[k];  // gravity as base acceleration
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; k++) { v[k] = S(L.o_vel + 6 * p + k); a[k] = S(L.o_acc + 6 * p + k); }
+    }
+    float vf[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) vf[k] = v[k];
+#pragma unroll 1
+    for (int d = d0; d < d1; d++) {
+      const int j = m->dof_jnt[d], kk = d - m->jnt_dadr[j];
+      const float qv = S(L.o_qvel + d);
+      const bool isfree = m->jnt_type[j] == MMZ_JNT_FREE;
+      if (isfree && kk < 3) {  // world-aligned translation: no axis derivative
+#pragma unroll
+        for (int k = 0; k < 3; k++) v[3 + k] += (k == kk) ? qv : 0.f;
+        if (kk == 2) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) vf[k] = v[k];
+        }
+        continue;
+      }
+      float s[6], sd[6], vs[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { s[k] = S(L.o_cdof + 6 * d + k); vs[k] = isfree ? vf[k] : v[k]; }
+      cross_motion(sd, vs, s);
+#pragma unroll
+      for (int i = 0; i < 6; i++) { a[i] += sd[i] * qv; v[i] += s[i] * qv; }
+    }
+    float Ia[6], Iv[6], vxIv[6];
+    inert_mul(Ia, Iw, a);
+    inert_mul(Iv, Iw, v);
+    cross_force(vxIv, v, Iv);
+#pragma unroll
+    for (int k = 0; k < 6; k++) { S(L.o_vel + 6 * b + k) = v[k]; S(L.o_acc + 6 * b + k) = a[k]; S(L.o_frc + 6 * b + k) = Ia[k] + vxIv[k]; }
+  }
+
+  // kinematics only (refresh of the derived arrays after a reset / set_state)
+  MMZ_DI void kinematics_only(const TLayout& L) {
+#pragma unroll 1
+    for (int lvl = 0; lvl < L.nlev; lvl++) {
+      for (int i = dv->lvl_off[lvl] + wid; i < dv->lvl_off[lvl + 1]; i += TW) body_pass(L, dv->lvl_body[i]);
+      __syncthreads();
+    }
+  }
+
+  // ------------------------------------------------------------------ phase B tasks
+  MMZ_DI void geom_pose(const TLayout& L, int g) {  // centre and long (local z) axis: all spheres and capsules need
+    const int b = m->geom_body[g];
+    float Rb[9], p[3], Rg[9], az[3], ax[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rb[k] = S(L.o_xmat + 9 * b + k);
+    mat_vec(p, Rb, m->geom_pos[g]);
+    quat2mat(Rg, m->geom_quat[g]);
+    az[0] = Rg[2]; az[1] = Rg[5]; az[2] = Rg[8];
+    mat_vec(ax, Rb, az);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { S(L.o_gpos + 3 * g + k) = p[k] + S(L.o_xpos + 3 * b + k); S(L.o_gax + 3 * g + k) = ax[k]; }
+  }
+  // sum over the subtree rooted at b of n-float records
+  MMZ_DI void subtree_sum(const TLayout& L, int b, int src, int dst, int n) {
+    float acc[10];
+    for (int k = 0; k < n; k++) acc[k] = S(src + n * b + k);
+#pragma unroll 1
+    for (int c = b + 1; c < L.nb; c++)
+      if (dv->anc[c] >> b & 1)
+        for (int k = 0; k < n; k++) acc[k] += S(src + n * c + k);
+    for (int k = 0; k < n; k++) S(dst + n * b + k) = acc[k];
+  }
+
+  // ------------------------------------------------------------------ phase C tasks
+  // row i of the mass matrix (composite rigid body): M[i][j] for the ancestors j of dof i
+  MMZ_DI void mass_row(const TLayout& L, int i) {
+    float Ic[10], ci[6], f[6];
+    const int b = m->dof_body[i];
+#pragma unroll
+    for (int k = 0; k < 10; k++) Ic[k] = S(L.o_ic + 10 * b + k);
+#pragma unroll
+    for (int k = 0; k < 6; k++) ci[k] = S(L.o_cdof + 6 * i + k);
+    inert_mul(f, Ic, ci);
+#pragma unroll 1
+    for (int j = i; j >= 0; j = m->dof_parent[j]) {
+      float cj[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) cj[k] = S(L.o_cdof + 6 * j + k);
+      float v = dot6(cj, f);
+      if (j == i) v += m->dof_armature[i];
+      S(L.o_M + i * L.ldm + j) = v;
+      S(L.o_M + j * L.ldm + i) = v;
+    }
+  }
+  // qfrc_smooth[d] = passive - bias + actuation
+  MMZ_DI void smooth_dof(const TLayout& L, int d) {
+    float cd[6], fs[6];
+    const int b = m->dof_body[d];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { cd[k] = S(L.o_cdof + 6 * d + k); fs[k] = S(L.o_fsub + 6 * b + k); }
+    const float bias = dot6(cd, fs);
+    const float passive = -m->dof_damping[d] * S(L.o_qvel + d);
+    float act = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < L.nu; k++)
+      if (m->act_dof[k] == d) {
+        float c = S(L.o_ctrl + k);
+        if (m->act_limited[k]) c = fminf(fmaxf(c, m->act_ctrlrange[k][0]), m->act_ctrlrange[k][1]);
+        act += m->act_gear[k] * c;
+      }
+    S(L.o_smooth + d) = passive - bias + act;
+  }
+
+  MMZ_DI void mix_params(int g, bool floor, float* par /* margin, mu, solref[2], solimp[5] */) const {
+    const float om = floor ? m->floor_margin : m->wall_margin, of = floor ? m->floor_friction[0] : m->wall_friction[0];
+    const float* osr = floor ? m->floor_solref : m->wall_solref;
+    const float* osi = floor ? m->floor_solimp : m->wall_solimp;
+    par[0] = fmaxf(m->geom_margin[g], om);
+    par[1] = fmaxf(m->geom_friction[g][0], of);
+#pragma unroll
+    for (int k = 0; k < 2; k++) par[2 + k] = 0.5f * (m->geom_solref[g][k] + osr[k]);
+#pragma unroll
+    for (int k = 0; k < 5; k++) par[4 + k] = 0.5f * (m->geom_solimp[g][k] + osi[k]);
+  }
+  MMZ_DI void cell_range(const float* c, const float* ext, int* i0, int* i1, int* j0, int* j1) const {
+    const float s = m->cell_size, hs = m->wall_half[0];
+    *j0 = max(0, (int)ceilf((c[0] - ext[0] + m->origin[0] - hs) / s));
+    *j1 = min(m->grid_w - 1, (int)floorf((c[0] + ext[0] + m->origin[0] + hs) / s));
+    *i0 = max(0, (int)ceilf((c[1] - ext[1] + m->origin[1] - hs) / s));
+    *i1 = min(m->grid_h - 1, (int)floorf((c[1] + ext[1] + m->origin[1] + hs) / s));
+  }
+  // stores a narrow-phase record into contact slot `slot` (layout C_* of mmz_layout.h)
+  MMZ_DI void write_contact(const TLayout& L, int slot, const RawContact& rc, int body, float sign, int g, bool floor) {
+    const int o = L.o_con + slot * L.cstride;
+    float fr[9], par[9];
+    mix_params(g, floor, par);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { fr[k] = rc.normal[k]; fr[3 + k] = rc.hint[k]; }
+    make_frame(fr);
+#pragma unroll
+    for (int k = 0; k < 3; k++) S(o + C_POS + k) = rc.pos[k];
+#pragma unroll
+    for (int k = 0; k < 9; k++) S(o + C_FRAME + k) = fr[k];
+    S(o + C_DIST) = rc.dist;
+    S(o + C_MARGIN) = par[0];
+    S(o + C_MU) = par[1];
+#pragma unroll
+    for (int k = 0; k < 7; k++) S(o + C_SOLREF + k) = par[2 + k];
+    S(o + C_INVW) = m->geom_invweight[g];
+    // geom1 -> geom2: the floor plane is geom1 of its pairs, a maze box is geom2
+    S(o + C_BODY1) = __int_as_float(sign > 0.f ? -1 : body);
+    S(o + C_BODY2) = __int_as_float(sign > 0.f ? body : -1);
+  }
+  // Contacts of sphere / capsule geom g against the floor plane and the maze boxes near it. pass 0 counts
+  // (into o_gcnt), pass 1 writes them at the slots following those of the geoms before it: the order is
+  // (geom, floor first, then cells row-major, wall before platform), independent of warp timing.
+  MMZ_DI void geom_contacts(const TLayout& L, int g, int pass) {
+    const int type = m->geom_type[g];
+    const bool capsule = type == MMZ_GEOM_CAPSULE;
+    int n = 0, base = 0;
+    if (pass == 1) {
+#pragma unroll 1
+      for (int gg = 0; gg < g; gg++) base += I(L.o_gcnt + gg);
+    }
+    const bool valid = (type == MMZ_GEOM_SPHERE || capsule) && ((m->geom_contype[g] | m->geom_conaffinity[g]) & 1) && m->collision_on;
+    if (valid) {
+      const float r = m->geom_size[g][0], gmarg = m->geom_margin[g];
+      const int body = m->geom_body[g];
+      float gp[3], axv[3], p0[3], p1[3], ext[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { gp[k] = S(L.o_gpos + 3 * g + k); axv[k] = S(L.o_gax + 3 * g + k); }
+      const float hl = capsule ? m->geom_size[g][1] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { const float a = axv[k] * hl; p0[k] = gp[k] + a; p1[k] = gp[k] - a; ext[k] = fabsf(a); }
+      // ---- floor plane (normal +z); geom1 = plane, geom2 = this geom
+      if (m->has_floor) {
+        const float margin = fmaxf(gmarg, m->floor_margin);
+        const float d0 = p0[2] - m->floor_z - r, d1 = p1[2] - m->floor_z - r;
+        float hint[3] = {0.f, 0.f, 0.f};
+        if (capsule && fabsf(axv[2]) <= 0.999999f) { hint[0] = axv[0]; hint[1] = axv[1]; hint[2] = axv[2]; }  // first tangent along the axis
+#pragma unroll 1
+        for (int end = 0; end < 2; end++) {
+          const float d = end == 0 ? d0 : d1;
+          if ((end == 1 && !capsule) || !(d < margin)) continue;
+          if (pass == 1 && base + n < L.maxcon) {
+            RawContact rc;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { rc.pos[k] = end == 0 ? p0[k] : p1[k]; rc.normal[k] = (k == 2) ? 1.f : 0.f; rc.hint[k] = hint[k]; }
+            rc.dist = d; rc.pos[2] -= r + 0.5f * d;
+            write_contact(L, base + n, rc, body, 1.f, g, true);
+          }
+          n++;
+        }
+      }
+      // ---- maze boxes; geom1 = this geom, geom2 = box (normal points from the geom into the box)
+      const float mg = r + fmaxf(gmarg, m->wall_margin);
+      ext[0] += mg; ext[1] += mg;
+      int i0, i1, j0, j1;
+      cell_range(gp, ext, &i0, &i1, &j0, &j1);
+      const int nslot = m->elevated ? 2 : 1;
+      const float margin = fmaxf(gmarg, m->wall_margin);
+#pragma unroll 1
+      for (int i = i0; i <= i1; i++)
+#pragma unroll 1
+        for (int j = j0; j <= j1; j++) {
+          const int code = m->grid[i * m->grid_w + j];
+#pragma unroll 1
+          for (int slot = 0; slot < nslot; slot++) {
+            if (!(code & (slot == 0 ? MMZ_CELL_WALL : MMZ_CELL_PLATFORM))) continue;
+            const float bc[3] = {j * m->cell_size - m->origin[0], i * m->cell_size - m->origin[1], slot == 0 ? m->wall_z : m->plat_z};
+            // capsule: both end caps when both are within the margin, otherwise the segment point nearest the box
+            RawContact r0, r1;
+            int n0 = sphere_box(p0, r, bc, dv->ident, m->wall_half, margin, &r0), n1 = 0;
+            if (capsule) {
+              n1 = sphere_box(p1, r, bc, dv->ident, m->wall_half, margin, &r1);
+              if (!(n0 && n1)) {
+                const float ts = capsule_nearest(p0, p1, bc, dv->ident, m->wall_half);
+                float pt[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) pt[k] = p0[k] + ts * (p1[k] - p0[k]);
+                n0 = sphere_box(pt, r, bc, dv->ident, m->wall_half, margin, &r0);
+                n1 = 0;
+              }
+            }
+            if (n0) { if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r0, body, -1.f, g, false); n++; }
+            if (n1) { if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r1, body, -1.f, g, false); n++; }
+          }
+        }
+    }
+    if (pass == 0) I(L.o_gcnt + g) = n;
+  }
+
+  MMZ_DI static float impedance(const float* si, float r) {
+    const float d0 = fminf(fmaxf(si[0], 1e-4f), 0.9999f), d1 = fminf(fmaxf(si[1], 1e-4f), 0.9999f);
+    const float width = si[2], mid = si[3], power = si[4];
+    if (d0 == d1 || width <= kMinVal) return 0.5f * (d0 + d1);
+    const float x = fabsf(r) / width;
+    float y;
+    if (x >= 1.f) return d1;
+    if (x <= 0.f) return d0;
+    if (power == 1.f) y = x;
+    else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.f);
+    else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+    return d0 + y * (d1 - d0);
+  }
+  MMZ_DI void row_params(const float* solref, const float* solimp, float pos, float margin, float diag, float* D, float* kr,
+                         float* bb) const {
+    const float tc = fmaxf(solref[0], 2.f * m->timestep), dr = solref[1];  // refsafe
+    const float dmax = fminf(fmaxf(solimp[1], 1e-4f), 0.9999f);
+    const float k = 1.f / fmaxf(kMinVal, dmax * dmax * tc * tc * dr * dr);
+    *bb = 2.f / fmaxf(kMinVal, dmax * tc);
+    const float imp = impedance(solimp, pos - margin);
+    const float R = fmaxf(kMinVal, (1.f - imp) * diag / imp);
+    *D = 1.f / R;
+    *kr = k * imp * (pos - margin);
+  }
+  // contact slot c (tree view): narrow-phase record -> D, aref[4], signed dof masks, point relative to the
+  // reference. J qvel is the point velocity of body2 minus body1, from the body velocities RNE has computed.
+  MMZ_DI void contact_rows(const TLayout& L, int c) {
+    if (c >= I(L.o_cnt + TN_CON)) return;
+    const int o = L.o_con + c * L.cstride;
+    float rf[3], cp[3], fr[9], solref[2], solimp[5], v[3] = {0.f, 0.f, 0.f};
+    ref(L, rf);
+#pragma unroll
+    for (int k = 0; k < 3; k++) cp[k] = S(o + C_POS + k) - rf[k];
+#pragma unroll
+    for (int k = 0; k < 9; k++) fr[k] = S(o + C_FRAME + k);
+    const float dist = S(o + C_DIST), margin = S(o + C_MARGIN), invw = S(o + C_INVW), mu = S(o + C_MU);
+#pragma unroll
+    for (int k = 0; k < 2; k++) solref[k] = S(o + C_SOLREF + k);
+#pragma unroll
+    for (int k = 0; k < 5; k++) solimp[k] = S(o + C_SOLIMP + k);
+    const int b1 = __float_as_int(S(o + C_BODY1)), b2 = __float_as_int(S(o + C_BODY2));
+    const int mask1 = b1 >= 0 ? m->body_dofmask[b1] : 0, mask2 = b2 >= 0 ? m->body_dofmask[b2] : 0;
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+      const int b = side == 0 ? b2 : b1;
+      if (b < 0) continue;
+      float bv[6], wxp[3];
+#pragma unroll
+      for (int k = 0; k < 6; k++) bv[k] = S(L.o_vel + 6 * b + k);
+      cross3(wxp, bv, cp);
+      const float sg = side == 0 ? 1.f : -1.f;
+#pragma unroll
+      for (int k = 0; k < 3; k++) v[k] += sg * (bv[3 + k] + wxp[k]);
+    }
+    const float jv0 = dot3(fr, v), jv1 = dot3(fr + 3, v), jv2 = dot3(fr + 6, v);
+    float D, kr, bb;
+    row_params(solref, solimp, dist, margin, invw * (1.f + mu * mu), &D, &kr, &bb);
+#pragma unroll
+    for (int k = 0; k < 3; k++) S(o + C_POS + k) = cp[k];
+    S(o + C_MPOS) = __int_as_float(mask2 & ~mask1);
+    S(o + C_MNEG) = __int_as_float(mask1 & ~mask2);
+    // all edges of the pyramid share R = 2 mu^2 R_first
+    S(o + C_D) = 1.f / fmaxf(kMinVal, 2.f * mu * mu / D);
+    S(o + C_AREF + 0) = -bb * (jv0 + mu * jv1) - kr;
+    S(o + C_AREF + 1) = -bb * (jv0 - mu * jv1) - kr;
+    S(o + C_AREF + 2) = -bb * (jv0 + mu * jv2) - kr;
+    S(o + C_AREF + 3) = -bb * (jv0 - mu * jv2) - kr;
+  }
+
+  // ================================================================== solver view (16 lanes = one environment)
+  MMZ_DI unsigned gballot(bool p) const { return (__ballot_sync(kAll, p) >> gshift) & 0xffffu; }
+  MMZ_DI static float gsum16(float v) {
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(kAll, v, off);
+    return v;
+  }
+  // joint-limit rows of this lane's dof, in registers: side 0 = lower (J = +1), side 1 = upper (J = -1)
+  MMZ_DI void limit_rows_g(const TLayout& L) {
+    limD[0] = limD[1] = 0.f; limA[0] = limA[1] = 0.f;
+    const int jl = lane < L.nv ? m->dof_jnt[lane] : 0;
+    const bool limited = lane < L.nv && m->jnt_limited[jl] && m->jnt_type[jl] >= MMZ_JNT_SLIDE;
+#pragma unroll 1
+    for (int s = 0; s < 2; s++) {
+      if (!limited) continue;
+      const float q = W_(L.o_qpos + m->jnt_qadr[jl]);
+      const float pos = s == 0 ? q - m->jnt_range[jl][0] : m->jnt_range[jl][1] - q, margin = m->jnt_margin[jl];
+      if (pos < margin) {
+        float D, kr, bb;
+        row_params(m->jnt_solref[jl], m->jnt_solimp[jl], pos, margin, m->dof_invweight0[lane], &D, &kr, &bb);
+        limD[s] = D;
+        limA[s] = -bb * (s == 0 ? 1.f : -1.f) * W_(L.o_qvel + lane) - kr;
+      }
+    }
+  }
+  // Lane i holds row i of the symmetric positive-definite H (NVP registers) and element i of the right-hand
+  // side: Gaussian elimination without pivoting, pivot row broadcast by shuffles, then back substitution.
+  MMZ_DI float elim_solve(float (&h)[NVP], float rhs, int nv) const {
+    float invd = 1.f;
+#pragma unroll
+    for (int j = 0; j < NVP; j++) {
+      if (j < nv) {
+        const float piv = fmaxf(__shfl_sync(kAll, h[j], j, 16), kMinVal);
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv));
+        inv = inv * (2.f - piv * inv);
+        const float rj = __shfl_sync(kAll, rhs, j, 16);
+        const float f = (lane > j) ? h[j] * inv : 0.f;
+        if (lane == j) invd = inv;
+        rhs -= f * rj;
+#pragma unroll
+        for (int k = j + 1; k < NVP; k++) h[k] -= f * __shfl_sync(kAll, h[k], j, 16);
+      }
+    }
+    float x = rhs;
+#pragma unroll
+    for (int j = NVP - 1; j >= 0; j--) {
+      if (j < nv) {
+        const float xj = __shfl_sync(kAll, x * invd, j, 16);
+        x = (lane == j) ? xj : ((lane < j) ? x - h[j] * xj : x);
+      }
+    }
+    return x;
+  }
+  // this lane's column of the contact-frame Jacobian of the contact block at slot offset cs
+  MMZ_DI void contact_jac(int cs, const float (&cd)[6], float* jn, float* jt1, float* jt2) const {
+    const int mp = __float_as_int(W_(cs + C_MPOS)), mn = __float_as_int(W_(cs + C_MNEG));
+    const float s = (float)(mp >> lane & 1) - (float)(mn >> lane & 1);
+    float p[3], fr[9], wxp[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) p[k] = W_(cs + C_POS + k);
+#pragma unroll
+    for (int k = 0; k < 9; k++) fr[k] = W_(cs + C_FRAME + k);
+    cross3(wxp, cd, p);
+    const float v[3] = {s * (cd[3] + wxp[0]), s * (cd[4] + wxp[1]), s * (cd[5] + wxp[2])};
+    *jn = dot3(fr, v); *jt1 = dot3(fr + 3, v); *jt2 = dot3(fr + 6, v);
+  }
+  MMZ_DI void contact_products(const TLayout& L, const float (&cd)[6], float x, int ncon, int ncw, int which, float* grad,
+                               float* mag) {
+#pragma unroll 1
+    for (int c = 0; c < ncw; c++) {
+      const int cs = L.o_con + c * L.cstride;
+      const bool valid = c < ncon;
+      float jn, jt1, jt2;
+      contact_jac(cs, cd, &jn, &jt1, &jt2);
+      if (!valid) { jn = 0.f; jt1 = 0.f; jt2 = 0.f; }
+      const float mu = valid ? W_(cs + C_MU) : 0.f;
+      float s0 = jn * x, s1 = jt1 * x, s2 = jt2 * x, sa = (fabsf(jn) + mu * (fabsf(jt1) + fabsf(jt2))) * fabsf(x);
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) {
+        s0 += __shfl_xor_sync(kAll, s0, off);
+        s1 += __shfl_xor_sync(kAll, s1, off);
+        s2 += __shfl_xor_sync(kAll, s2, off);
+        if (which == 0) sa += __shfl_xor_sync(kAll, sa, off);
+      }
+      if (!valid) continue;  // no shuffles below
+      const float e0 = s0 + mu * s1, e1 = s0 - mu * s1, e2 = s0 + mu * s2, e3 = s0 - mu * s2;
+      if (which == 0) {
+        const float r0 = W_(cs + C_AREF), r1 = W_(cs + C_AREF + 1), r2 = W_(cs + C_AREF + 2), r3 = W_(cs + C_AREF + 3);
+        const float j0 = e0 - r0, j1 = e1 - r1, j2 = e2 - r2, j3 = e3 - r3;
+        if (lane == 0) { W_(cs + C_JAR) = j0; W_(cs + C_JAR + 1) = j1; W_(cs + C_JAR + 2) = j2; W_(cs + C_JAR + 3) = j3; }
+        const float a0 = j0 < 0.f, a1 = j1 < 0.f, a2 = j2 < 0.f, a3 = j3 < 0.f;
+        const float D = W_(cs + C_D);
+        const float f0 = a0 * D * j0, f1 = a1 * D * j1, f2 = a2 * D * j2, f3 = a3 * D * j3;
+        *grad += jn * (f0 + f1 + f2 + f3) + jt1 * (mu * (f0 - f1)) + jt2 * (mu * (f2 - f3));
+        const float bound = sa + fmaxf(fmaxf(fabsf(r0), fabsf(r1)), fmaxf(fabsf(r2), fabsf(r3)));
+        *mag += D * bound * ((a0 + a1 + a2 + a3) * fabsf(jn) + mu * ((a0 + a1) * fabsf(jt1) + (a2 + a3) * fabsf(jt2)));
+      } else if (lane == 0) {
+        W_(cs + C_JV) = e0; W_(cs + C_JV + 1) = e1; W_(cs + C_JV + 2) = e2; W_(cs + C_JV + 3) = e3;
+      }
+    }
+  }
+  // Newton solver (mj_solNewton), lanes <-> dofs; same algorithm as mmz_dyn.cuh: Env::solve
+  MMZ_DI void solve_g(const TLayout& L, bool warmstart) {
+    const int nv = L.nv, ncon = IW(L.o_cnt + TN_CON);
+    int ncw = max(ncon, __shfl_xor_sync(kAll, ncon, 16));  // the two environments of the warp
+    const bool me = lane < nv;
+    const unsigned limbits = gballot(limD[0] > 0.f || limD[1] > 0.f);
+    const bool constrained = ncon > 0 || limbits != 0;
+    float cd[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) cd[k] = me ? W_(L.o_cdof + 6 * lane + k) : 0.f;
+    const float sm_ = me ? W_(L.o_smooth + lane) : 0.f;
+    float al = (warmstart && me) ? W_(L.o_qacc + lane) : 0.f;
+    if (!warmstart && me) W_(L.o_qacc + lane) = 0.f;
+    const int nlim = __popc(gballot(limD[0] > 0.f)) + __popc(gballot(limD[1] > 0.f));
+    if (lane == 0) {
+      IW(L.o_cnt + TN_ITER) = 0; IW(L.o_cnt + TN_LIM) = nlim;
+      IW(L.o_cnt + TN_CON_MAX) = max(IW(L.o_cnt + TN_CON_MAX), ncon);
+    }
+    __syncwarp();
+    bool done = false;
+#pragma unroll 1
+    for (int it = 0; it < kTMaxNewton; it++) {
+      float Ma = 0.f, mag = 0.f;
+      if (me) {
+#pragma unroll 2
+        for (int k = 0; k < nv; k++) { const float t = W_(L.o_M + lane * L.ldm + k) * W_(L.o_qacc + k); Ma += t; mag += fabsf(t); }
+      }
+      float grad = Ma - sm_, dadd = 0.f;
+      mag += fabsf(sm_);
+      float ljar[2];
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const float sign = s == 0 ? 1.f : -1.f;
+        ljar[s] = sign * al - limA[s];
+        if (limD[s] > 0.f && ljar[s] < 0.f) {
+          grad += limD[s] * ljar[s] * sign;
+          mag += limD[s] * (fabsf(al) + fabsf(limA[s]));
+          dadd += limD[s];
+        }
+      }
+      contact_products(L, cd, al, ncon, ncw, 0, &grad, &mag);
+      if (gballot(fabsf(grad) > 2e-6f * mag + 1e-30f) == 0) done = true;
+      if (__all_sync(kAll, done)) break;
+      __syncwarp();
+      float hrow[NVP];
+#pragma unroll
+      for (int k = 0; k < NVP; k++) {
+        const float mk = (me && k < nv) ? W_(L.o_M + lane * L.ldm + k) : 0.f;
+        hrow[k] = (k == lane) ? (me ? mk + dadd : 1.f) : mk;
+      }
+#pragma unroll 1
+      for (int c = 0; c < ncw; c++) {
+        const int cs = L.o_con + c * L.cstride;
+        const bool valid = c < ncon;
+        const float a0 = valid && W_(cs + C_JAR) < 0.f, a1 = valid && W_(cs + C_JAR + 1) < 0.f, a2 = valid && W_(cs + C_JAR + 2) < 0.f,
+                    a3 = valid && W_(cs + C_JAR + 3) < 0.f;
+        const bool act = a0 + a1 + a2 + a3 != 0.f;
+        if (!__any_sync(kAll, act)) continue;
+        float jn, jt1, jt2;
+        contact_jac(cs, cd, &jn, &jt1, &jt2);
+        if (!act) { jn = 0.f; jt1 = 0.f; jt2 = 0.f; }
+        const float D = act ? W_(cs + C_D) : 0.f, mu = act ? W_(cs + C_MU) : 0.f;
+        const float wnn = D * (a0 + a1 + a2 + a3), wn1 = D * mu * (a0 - a1), wn2 = D * mu * (a2 - a3);
+        const float w11 = D * mu * mu * (a0 + a1), w22 = D * mu * mu * (a2 + a3);
+        const float u0 = wnn * jn + wn1 * jt1 + wn2 * jt2, u1 = wn1 * jn + w11 * jt1, u2 = wn2 * jn + w22 * jt2;
+#pragma unroll
+        for (int k = 0; k < NVP; k++)
+          hrow[k] += u0 * __shfl_sync(kAll, jn, k, 16) + u1 * __shfl_sync(kAll, jt1, k, 16) + u2 * __shfl_sync(kAll, jt2, k, 16);
+      }
+      const float dr = elim_solve(hrow, me ? -grad : 0.f, nv);
+      if (me && !done) W_(L.o_dir + lane) = dr;
+      __syncwarp();
+      float alpha = 1.f;
+      int ls = 0;
+      if (__any_sync(kAll, constrained && !done)) {
+        float dummy0 = 0.f, dummy1 = 0.f;
+        contact_products(L, cd, dr, done ? 0 : ncon, ncw, 1, &dummy0, &dummy1);
+        __syncwarp();
+        float md = 0.f;
+        if (me) {
+#pragma unroll 2
+          for (int k = 0; k < nv; k++) md += W_(L.o_M + lane * L.ldm + k) * W_(L.o_dir + k);
+        }
+        const float g0 = gsum16(me ? dr * (Ma - sm_) : 0.f), h0 = gsum16(me ? dr * md : 0.f);
+        float lo = 0.f, hi = -1.f;
+        bool lsdone = done || !constrained;
+#pragma unroll 1
+        for (int k = 0; k < kTMaxLineSearch; k++) {
+          float g = 0.f, h = 0.f;
+#pragma unroll
+          for (int s = 0; s < 2; s++) {
+            const float jv = s == 0 ? dr : -dr, x = ljar[s] + alpha * jv;
+            if (limD[s] > 0.f && x < 0.f) { g += limD[s] * x * jv; h += limD[s] * jv * jv; }
+          }
+          if (!lsdone) {
+#pragma unroll 1
+            for (int r = lane; r < 4 * ncon; r += 16) {
+              const int cs = L.o_con + (r >> 2) * L.cstride;
+              const float jv = W_(cs + C_JV + (r & 3)), x = W_(cs + C_JAR + (r & 3)) + alpha * jv, D = W_(cs + C_D);
+              if (x < 0.f) { g += D * x * jv; h += D * jv * jv; }
+            }
+          }
+          g = gsum16(g) + g0 + alpha * h0;
+          h = gsum16(h) + h0;
+          if (!lsdone) {
+            if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) lsdone = true;
+            else {
+              if (g < 0.f) lo = alpha; else hi = alpha;
+              float next = alpha - g / h;
+              if (hi >= 0.f && (next <= lo || next >= hi)) next = 0.5f * (lo + hi);
+              if (next <= lo && hi < 0.f) next = 2.f * alpha + 1e-6f;
+              if (next == alpha) lsdone = true;
+              else { alpha = next; ls++; }
+            }
+          }
+          if (__all_sync(kAll, lsdone)) break;
+        }
+      }
+      bool moved = false;
+      if (me && !done) {
+        const float st = alpha * dr;
+        moved = fabsf(st) > 2e-6f * fabsf(al) + 1e-6f;
+        al += st;
+        W_(L.o_qacc + lane) = al;
+      }
+      if (lane == 0 && !done) {
+        IW(L.o_cnt + TN_ITER) = it + 1; IW(L.o_cnt + TN_ITER_SUM) += 1; IW(L.o_cnt + TN_LS_SUM) += ls;
+        if (it == kTMaxNewton - 1) IW(L.o_cnt + TN_CAPPED) += 1;
+      }
+      __syncwarp();
+      const unsigned movedbits = gballot(moved);
+      if (!constrained || movedbits == 0) done = true;
+      if (__all_sync(kAll, done)) break;
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------ mj_forward
+  MMZ_DI void forward(const TLayout& L, bool warmstart) {
+    // A: tree levels (kinematics, motion axes, world inertia, RNE forward)
+#pragma unroll 1
+    for (int lvl = 0; lvl < L.nlev; lvl++) {
+      for (int i = dv->lvl_off[lvl] + wid; i < dv->lvl_off[lvl + 1]; i += TW) body_pass(L, dv->lvl_body[i]);
+      __syncthreads();
+    }
+    // B: geom poses, composite inertias, subtree forces
+    {
+      const int nt = L.ng + 2 * L.nb;
+      for (int t = wid; t < nt; t += TW) {
+        if (t < L.ng) geom_pose(L, t);
+        else if (t < L.ng + L.nb) subtree_sum(L, t - L.ng, L.o_iw, L.o_ic, 10);
+        else subtree_sum(L, t - L.ng - L.nb, L.o_frc, L.o_fsub, 6);
+      }
+    }
+    __syncthreads();
+    // C: contact counting, mass matrix rows, smooth forces
+    {
+      const int nt = 2 * L.nv + L.ng;
+      for (int t = wid; t < nt; t += TW) {
+        if (t < L.ng) geom_contacts(L, t, 0);
+        else if (t < L.ng + L.nv) mass_row(L, t - L.ng);
+        else smooth_dof(L, t - L.ng - L.nv);
+      }
+    }
+    __syncthreads();
+    // D: contacts into their slots
+    for (int g = wid; g < L.ng; g += TW) geom_contacts(L, g, 1);
+    if (wid == TW - 1) {
+      int n = 0;
+#pragma unroll 1
+      for (int g = 0; g < L.ng; g++) n += I(L.o_gcnt + g);
+      I(L.o_cnt + TN_OVERFLOW) = n > L.maxcon ? 1 : 0;
+      I(L.o_cnt + TN_CON) = min(n, L.maxcon);
+    }
+    __syncthreads();
+    // E: contact rows
+    {
+      const int ncmax = __reduce_max_sync(kAll, I(L.o_cnt + TN_CON));
+      for (int c = wid; c < ncmax; c += TW) contact_rows(L, c);
+    }
+    __syncthreads();
+    // solver view: warp w owns environments w and w + 16
+    limit_rows_g(L);
+    solve_g(L, warmstart);
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ state checks
+  MMZ_DI bool state_bad(const TLayout& L) const {  // every thread evaluates its environment (cheap)
+    bool bad = false;
+#pragma unroll 1
+    for (int i = 0; i < L.nq; i++) bad |= !(fabsf(S(L.o_qpos + i)) < kMaxVal);
+#pragma unroll 1
+    for (int i = 0; i < L.nv; i++) bad |= !(fabsf(S(L.o_qvel + i)) < kMaxVal);
+    return bad;
+  }
+  MMZ_DI void park(const TLayout& L, bool on) {  // qpos0, zero velocity and acceleration
+    if (on) {
+      for (int i = wid; i < L.nq; i += TW) S(L.o_qpos + i) = m->qpos0[i];
+      for (int d = wid; d < L.nv; d += TW) { S(L.o_qvel + d) = 0.f; S(L.o_qacc + d) = 0.f; }
+    }
+  }
+
+  // ------------------------------------------------------------------ mj_step, RK4 (mj_RungeKutta)
+  // `dead`: the environment already blew up in this env-step; it is parked at qpos0 and keeps running.
+  MMZ_DI bool mj_step(const TLayout& L, bool dead) {
+    const float h = m->timestep;
+    const int nq = L.nq, nv = L.nv;
+    bool bad = dead || state_bad(L);
+    __syncthreads();
+    park(L, bad);
+    __syncthreads();
+    for (int i = wid; i < nq; i += TW) S(L.o_q0 + i) = S(L.o_qpos + i);
+    for (int d = wid; d < nv; d += TW) { S(L.o_v0 + d) = S(L.o_qvel + d); S(L.o_accv + d) = 0.f; S(L.o_acca + d) = 0.f; }
+    __syncthreads();
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+      forward(L, true);
+      // accumulate this stage, then move to the state of the next stage (or the final combination)
+      const float B = (i == 0 || i == 3) ? (1.f / 6.f) : (1.f / 3.f);
+      bool badacc = false;
+#pragma unroll 1
+      for (int d = 0; d < nv; d++) badacc |= !(fabsf(S(L.o_qacc + d)) < kMaxVal);
+      bad |= badacc;
+      __syncthreads();
+      for (int d = wid; d < nv; d += TW) {
+        float f = S(L.o_qacc + d);
+        if (badacc) { f = 0.f; S(L.o_qacc + d) = 0.f; }
+        S(L.o_accv + d) += B * S(L.o_qvel + d);
+        S(L.o_acca + d) += B * f;
+      }
+      __syncthreads();
+      const float A = (i == 0 || i == 1) ? 0.5f : 1.f;
+      const int vsrc = (i == 3) ? L.o_accv : L.o_qvel, asrc = (i == 3) ? L.o_acca : L.o_qacc;
+      // positions first (they read the stage velocity), on the configuration manifold (mj_integratePos)
+      for (int j = wid; j < L.nj; j += TW) {
+        const int qa = m->jnt_qadr[j], d = m->jnt_dadr[j];
+        if (m->jnt_type[j] == MMZ_JNT_FREE) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) S(L.o_qpos + qa + k) = S(L.o_q0 + qa + k) + h * A * S(vsrc + d + k);
+          float wv[3] = {A * S(vsrc + d + 3), A * S(vsrc + d + 4), A * S(vsrc + d + 5)};
+          float q[4] = {S(L.o_q0 + qa + 3), S(L.o_q0 + qa + 4), S(L.o_q0 + qa + 5), S(L.o_q0 + qa + 6)};
+          const float nw = norm3(wv), ang = h * nw;
+          quat_norm(q);
+          if (ang > 0.f) {
+            const float inv = 1.f / nw;
+            float ax[3] = {wv[0] * inv, wv[1] * inv, wv[2] * inv}, qr[4], q2[4];
+            axisangle2quat(qr, ax, ang);
+            quat_mul(q2, q, qr);
+#pragma unroll
+            for (int k = 0; k < 4; k++) q[k] = q2[k];
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) S(L.o_qpos + qa + 3 + k) = q[k];
+        } else {
+          S(L.o_qpos + qa) = S(L.o_q0 + qa) + h * A * S(vsrc + d);
+        }
+      }
+      __syncthreads();
+      for (int d = wid; d < nv; d += TW) S(L.o_qvel + d) = S(L.o_v0 + d) + h * A * S(asrc + d);
+      __syncthreads();
+    }
+    // derived arrays (xpos, contacts) deliberately stay at the 4th-stage state: SURVEY quirk Q15
+    return bad || state_bad(L);
+  }
+#undef S
+#undef W_
+};
+
+}  // namespace mmz
