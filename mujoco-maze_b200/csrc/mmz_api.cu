@@ -80,6 +80,7 @@ struct mmz_env {
   kernel_fn fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // hybrid kernel (mmz_hkernel.cuh), used when the model is eligible
   bool use_t = false;
+  float tol = 2e-6f;  // Newton convergence tolerance of the hybrid kernel (fp32 round-off floor)
   TLayout TL;
   mmz::hkernel_fn tfn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -167,7 +168,7 @@ int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s) {
     T.n = h->n; T.npad = h->npad;
     T.action = A.action; T.obs = A.obs; T.reward = A.reward; T.done = A.done; T.info = A.info;
     T.qacc_out = A.qacc_out; T.diag = A.diag; T.mask = A.mask; T.seed = A.seed;
-    T.flags = h->flags; T.env_offset = h->env_offset;
+    T.flags = h->flags; T.env_offset = h->env_offset; T.tol = h->tol;
     h->tfn[mode]<<<h->npad / TE, TW * 32, h->smem_bytes, s>>>(T);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -255,6 +256,7 @@ bool configure_h(mmz_env* h, int* rc) {
     if (e != cudaSuccess) { *rc = fail(MMZ_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return false; }
   }
   h->use_t = true;
+  if (const char* e = getenv("MMZ_TOL")) h->tol = (float)atof(e);  // development aid
   h->G = 16; h->NVP = m.nv <= 14 ? 14 : 16; h->tpb = TW * 32; h->envs_per_sm = TE;
   h->L.stride = L.nslots; h->L.nstate = L.nstate; h->L.model_bytes = L.model_bytes;
   return true;

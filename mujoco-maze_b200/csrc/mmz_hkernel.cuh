@@ -75,6 +75,7 @@ struct TArgs {
   unsigned long long seed;
   unsigned flags;
   int env_offset;
+  float tol;           // Newton convergence: |grad_d| <= tol * (magnitude of the terms grad_d is the sum of)
 };
 
 
@@ -88,6 +89,7 @@ struct HEnv {
   int e, wid;               // tree view: lane = environment e; warp wid takes items wid, wid + 16, ...
   int genv, lane, gshift;   // solver view: environment wid + 16 * (laneid / 16), lane = dof
   float limD[2], limA[2];   // this lane's joint-limit rows (solver view)
+  float tol;                // Newton convergence tolerance (relative to the magnitude of the cancelling terms)
 
 #define S(i) sm[(i) * HS + e]
 #define W_(i) sm[(i) * HS + genv]
@@ -660,7 +662,7 @@ struct HEnv {
         }
       }
       contact_products(L, cd, al, ncon, ncw, 0, &grad, &mag);
-      if (gballot(fabsf(grad) > 2e-6f * mag + 1e-30f) == 0) done = true;
+      if (gballot(fabsf(grad) > tol * mag + 1e-30f) == 0) done = true;
       if (__all_sync(kAll, done)) break;
       __syncwarp();
       float hrow[NVP];

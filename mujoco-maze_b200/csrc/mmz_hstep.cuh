@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
   T.genv = T.wid + 16 * (T.e >> 4);
   T.lane = T.e & 15;
   T.gshift = (T.e >> 4) * 16;
+  T.tol = A.tol;
   const int e = T.e, wid = T.wid;
 #define S(i) ws[(i) * HS + e]
   // the mass matrix is only ever written on its (static) sparsity pattern: clear it once
