@@ -647,22 +647,25 @@ struct Env {
     if constexpr ((FEAT & FEAT_BOX) != 0) {
 #pragma unroll 1
       for (int k = 0; k < dv->nboxg; k++) {
-        int g = dv->boxg[k];
-        if (lane == 0 && ((m->geom_contype[g] | m->geom_conaffinity[g]) & 1)) box_geom_contacts(L, g, k);
-        sync();
+        box_geom_contacts(L, dv->boxg[k], k);
       }
     }
   }
 
+  // Box geom g (Point's arrow, a movable block): its candidates - the floor, the maze boxes near it and the
+  // box geoms after it - are split over the lanes of the group (box-box is long, serial code); a scan over
+  // the lanes keeps the contact order (candidate-major) independent of the mapping. Warp-uniform call.
+  // (Same run, 20 steps: PointUMaze 4096 envs 0.42 -> 0.35 ms, AntPush 32768 envs 29.4 -> 26.1 ms per step.)
   __device__ __noinline__ void box_geom_contacts(const Layout& L, int g, int kbox) {
     int* cn = cnt(L);
     int ncon = cn[N_CON];
+    bool overflow = false;
+    const bool active = ((m->geom_contype[g] | m->geom_conaffinity[g]) & 1) != 0;
     const float* gp = w + L.o_gpos + 3 * g;
     const float* gm = w + L.o_gmat + 9 * g;
     const float* sz = m->geom_size[g];
     const int body = m->geom_body[g];
     const float invw = m->geom_invweight[g];
-    RawContact rc[8];
     float ext[3], wallmargin = fmaxf(m->geom_margin[g], m->wall_margin);
 #pragma unroll
     for (int k = 0; k < 3; k++) ext[k] = fabsf(gm[3 * k]) * sz[0] + fabsf(gm[3 * k + 1]) * sz[1] + fabsf(gm[3 * k + 2]) * sz[2];
@@ -671,47 +674,63 @@ struct Env {
     cell_range(gp, ext, &i0, &i1, &j0, &j1);
     const int nj = max(0, j1 - j0 + 1), ncell = nj * max(0, i1 - i0 + 1);
     // candidates: floor, then (cell, wall|platform) pairs, then later box geoms on other bodies
-    const int ncand = 1 + 2 * ncell + (dv->nboxg - kbox - 1);
-    for (int cand = 0; cand < ncand; cand++) {
+    const int ncand = active ? 1 + 2 * ncell + (dv->nboxg - kbox - 1) : 0;
+    const int ncandw = wmax(ncand);
+    constexpr int P = G;
+#pragma unroll 1
+    for (int cbase = 0; cbase < ncandw; cbase += P) {
+      const int cand = cbase + lane;
+      RawContact rc[8];
       int n = 0, b1 = -1, b2 = body, other = -1;
       float iw = invw;
-      if (cand == 0) {  // corners below the plane, at most 4; geom1 = plane
-        if (!m->has_floor) continue;
-        float margin = fmaxf(m->geom_margin[g], m->floor_margin);
-        for (int c = 0; c < 8 && n < 4; c++) {
-          float loc[3] = {(c & 1 ? 1.f : -1.f) * sz[0], (c & 2 ? 1.f : -1.f) * sz[1], (c & 4 ? 1.f : -1.f) * sz[2]}, wp[3];
-          mat_vec(wp, gm, loc);
-          float dist = wp[2] + gp[2] - m->floor_z;
-          if (dist < margin) {
-            rc[n].dist = dist;
-            rc[n].pos[0] = wp[0] + gp[0]; rc[n].pos[1] = wp[1] + gp[1]; rc[n].pos[2] = wp[2] + gp[2] - 0.5f * dist;
-            rc[n].normal[0] = 0.f; rc[n].normal[1] = 0.f; rc[n].normal[2] = 1.f;
-            rc[n].hint[0] = rc[n].hint[1] = rc[n].hint[2] = 0.f;
-            n++;
+      if (lane < P && cand < ncand) {
+        if (cand == 0) {  // corners below the plane, at most 4; geom1 = plane
+          if (m->has_floor) {
+            float margin = fmaxf(m->geom_margin[g], m->floor_margin);
+            for (int c = 0; c < 8 && n < 4; c++) {
+              float loc[3] = {(c & 1 ? 1.f : -1.f) * sz[0], (c & 2 ? 1.f : -1.f) * sz[1], (c & 4 ? 1.f : -1.f) * sz[2]}, wp[3];
+              mat_vec(wp, gm, loc);
+              float dist = wp[2] + gp[2] - m->floor_z;
+              if (dist < margin) {
+                rc[n].dist = dist;
+                rc[n].pos[0] = wp[0] + gp[0]; rc[n].pos[1] = wp[1] + gp[1]; rc[n].pos[2] = wp[2] + gp[2] - 0.5f * dist;
+                rc[n].normal[0] = 0.f; rc[n].normal[1] = 0.f; rc[n].normal[2] = 1.f;
+                rc[n].hint[0] = rc[n].hint[1] = rc[n].hint[2] = 0.f;
+                n++;
+              }
+            }
+          }
+        } else if (cand - 1 < 2 * ncell) {  // maze boxes; geom1 = wall (lower geom id), geom2 = this box
+          int ci = (cand - 1) >> 1, slot = (cand - 1) & 1;
+          int i = i0 + ci / nj, j = j0 + ci % nj;
+          int code = m->grid[i * m->grid_w + j];
+          if (code & (slot == 0 ? MMZ_CELL_WALL : MMZ_CELL_PLATFORM)) {
+            float bc[3] = {j * m->cell_size - m->origin[0], i * m->cell_size - m->origin[1], slot == 0 ? m->wall_z : m->plat_z};
+            other = -2;
+            n = box_box(bc, dv->ident, m->wall_half, gp, gm, sz, wallmargin, rc);
+          }
+        } else {  // box against box on different moving bodies
+          int g2 = dv->boxg[kbox + 1 + (cand - 1 - 2 * ncell)];
+          if (moving_pair_ok(g, g2)) {
+            other = g2; b1 = body; b2 = m->geom_body[g2];
+            iw = invw + m->geom_invweight[g2];
+            n = box_box(gp, gm, sz, w + L.o_gpos + 3 * g2, w + L.o_gmat + 9 * g2, m->geom_size[g2],
+                        fmaxf(m->geom_margin[g], m->geom_margin[g2]), rc);
           }
         }
-      } else if (cand - 1 < 2 * ncell) {  // maze boxes; geom1 = wall (lower geom id), geom2 = this box
-        int ci = (cand - 1) >> 1, slot = (cand - 1) & 1;
-        int i = i0 + ci / nj, j = j0 + ci % nj;
-        int code = m->grid[i * m->grid_w + j];
-        if (!(code & (slot == 0 ? MMZ_CELL_WALL : MMZ_CELL_PLATFORM))) continue;
-        float bc[3] = {j * m->cell_size - m->origin[0], i * m->cell_size - m->origin[1], slot == 0 ? m->wall_z : m->plat_z};
-        other = -2;
-        n = box_box(bc, dv->ident, m->wall_half, gp, gm, sz, wallmargin, rc);
-      } else {  // box against box on different moving bodies
-        int g2 = dv->boxg[kbox + 1 + (cand - 1 - 2 * ncell)];
-        if (!moving_pair_ok(g, g2)) continue;
-        other = g2; b1 = body; b2 = m->geom_body[g2];
-        iw = invw + m->geom_invweight[g2];
-        n = box_box(gp, gm, sz, w + L.o_gpos + 3 * g2, w + L.o_gmat + 9 * g2, m->geom_size[g2],
-                    fmaxf(m->geom_margin[g], m->geom_margin[g2]), rc);
       }
+      if (!__any_sync(kFull, n > 0)) continue;
+      int total, incl = gscan<G>(n, lane, &total);
+      const int base = ncon + incl - n;
       for (int k = 0; k < n; k++) {
-        if (ncon < L.maxcon) write_contact(L, ncon++, rc[k], b1, b2, iw, g, other);
-        else cn[N_OVERFLOW] = 1;
+        if (base + k < L.maxcon) write_contact(L, base + k, rc[k], b1, b2, iw, g, other);
       }
+      ncon += total;
+      if (ncon > L.maxcon) { ncon = L.maxcon; overflow = true; }
     }
-    cn[N_CON] = ncon;
+    sync();
+    if (lane == 0) { cn[N_CON] = ncon; if (overflow) cn[N_OVERFLOW] = 1; }
+    sync();
   }
 
   // ---------------------------------------------------------------- constraint rows (mj_makeConstraint)
