@@ -285,10 +285,10 @@ void make_tderived(const mmz_model& m, TDerived* d) {
 int configure(mmz_env* h, int G, int NVP) {
   h->G = G;
   h->NVP = NVP;
-  // contact capacity: generous for box geoms (up to 8 points per box pair), 16 otherwise
+  // contact capacity: generous for box geoms (up to 8 points per box pair and several pairs per block), 16 otherwise
   int nbox = 0;
   for (int g = 0; g < h->hm.ngeom; g++) nbox += h->hm.geom_type[g] == MMZ_GEOM_BOX;
-  int maxcon = h->hm.collision_on ? (nbox ? 24 : 16) : 1;
+  int maxcon = h->hm.collision_on ? (nbox ? std::min(40, 16 + 8 * nbox) : 16) : 1;  // 1 block: 24, 2: 32, 3+: 40
   if (h->hm.ngeom <= 2 && nbox) maxcon = 16;
   make_layout(h->hm, G, NVP, maxcon, &h->L);
   int dev_smem = 0, sms = 0;

@@ -21,7 +21,10 @@ from conftest import ROOT, make_model
 
 pytestmark = pytest.mark.gpu
 
-ENV_IDS = ["PointUMaze-v0", "SwimmerUMaze-v0", "AntUMaze-v0", "Ant4Rooms-v0", "AntPush-v0", "Point4Rooms-v1", "PointPush-v0"]
+ENV_IDS = ["PointUMaze-v0", "SwimmerUMaze-v0", "AntUMaze-v0", "Ant4Rooms-v0", "AntPush-v0", "Point4Rooms-v1", "PointPush-v0",
+           # beyond the BASELINE configs: elevated mazes with platforms and a z-slide block, several
+           # blocks (18 dofs: the one-warp-per-environment instance), sub-goal and object-distance rewards
+           "AntFall-v0", "PointFall-v0", "AntMultiPush-v0", "Ant2Rooms-v2", "PointBlockCarry-v0", "PointPushMaze-v1"]
 OUT = os.path.join(ROOT, "gpurun_out", "parity")
 
 
@@ -48,7 +51,7 @@ def sample_states(model, env_id, n, rng):
     s = float(model.cell_size)
     if env_id.startswith("Ant"):
         q[:, 0:2] = rng.uniform(-0.45 * s, 0.45 * s, size=(n, 2))
-        q[:, 2] = rng.uniform(0.3, 0.95, size=n)
+        q[:, 2] = float(model.qpos0[2]) - 0.75 + rng.uniform(0.3, 0.95, size=n)  # elevated mazes start on the platforms
         quat = np.concatenate([np.ones((n, 1)), rng.normal(scale=0.25, size=(n, 3))], axis=1)
         q[:, 3:7] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
         q[:, 7:15] += rng.uniform(-0.7, 0.7, size=(n, 8))

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Builds mujoco-maze_b200/libmmz_dbg.so with -DMMZ_DEBUG_UNIFORM (prints where a warp's control flow diverged).
-Use: MMZ_LIB=libmmz_dbg.so python tools/probe_rollout.py ... (development aid)."""
+"""Builds mujoco-maze_b200/libmmz_dbg.so with extra -D flags (development aid), e.g.
+    python tools/build_debug.py -DMMZ_PHASE_TIMING      # cycles per phase of block 0 of the hybrid kernel
+    python tools/build_debug.py -DMMZ_DEBUG_UNIFORM     # prints where a warp's control flow diverged (mmz_dyn.cuh)
+Use: MMZ_LIB=libmmz_dbg.so python bench.py ..."""
 import concurrent.futures as cf
 import os
 import subprocess
@@ -11,10 +13,13 @@ PKG = os.path.join(ROOT, "mujoco-maze_b200")
 sys.path.insert(0, PKG)
 from build_native import INSTANCES  # noqa: E402
 
-flags = "-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DMMZ_DEBUG_UNIFORM".split()
+extra = [a for a in sys.argv[1:] if a.startswith("-D")] or ["-DMMZ_DEBUG_UNIFORM"]
+flags = "-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC".split() + extra
 jobs = [(os.path.join(PKG, "csrc/mmz_api.cu"), "/tmp/dbg_api.o", [])]
 for g, n, f in INSTANCES:
     jobs.append((os.path.join(PKG, "csrc/mmz_inst.cu"), f"/tmp/dbg_{g}_{n}_{f}.o", [f"-DMMZ_G={g}", f"-DMMZ_NVP={n}", f"-DMMZ_FEAT={f}"]))
+for n in (14, 16):
+    jobs.append((os.path.join(PKG, "csrc/mmz_hinst.cu"), f"/tmp/dbg_h{n}.o", [f"-DMMZ_NVP={n}"]))
 
 
 def run(j):
