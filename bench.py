@@ -334,7 +334,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_env_step": algorithmic_bytes_per_env_step(model),
-                         "kernel": "maze_kernel<G,NVP,MODE_STEP>",
+                         "kernel": sim.kernel_config.get("kernel", "maze_kernel"),
                          "note": "nominal bound; the step is fp32-issue / latency bound (about 1 MFLOP per Ant env-step "
                                  "against 0.5 KB of HBM traffic), see DESIGN.md"},
         }

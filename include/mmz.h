@@ -73,6 +73,10 @@ int mmz_dims(mmz_handle h, int* num_envs, int* nq, int* nv, int* nu, int* obs_di
 int mmz_kernel_config(mmz_handle h, int* lanes_per_env, int* threads_per_block, int* smem_bytes, int* envs_per_sm,
                       int* floats_per_env);
 
+/* Name of the step kernel this handle launches: "maze_hkernel<14>" (hybrid: tree phases lane = environment,
+ * solver 16 lanes per environment) or "maze_kernel<G,NVP,FEAT>" (G lanes per environment). Static string. */
+const char* mmz_kernel_name(mmz_handle h);
+
 /* Multi-GPU sharding: this handle holds environments [first_global_env, first_global_env + N)
  * of a larger batch. Only the reset noise depends on it (Philox streams are keyed by the GLOBAL
  * environment index), so 1 GPU x N and G GPUs x N/G give identical results. There is no

@@ -80,6 +80,7 @@ struct mmz_env {
   kernel_fn fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   // hybrid kernel (mmz_hkernel.cuh), used when the model is eligible
   bool use_t = false;
+  char kname[48] = "";
   float tol = 2e-6f;  // Newton convergence tolerance of the hybrid kernel (fp32 round-off floor)
   TLayout TL;
   mmz::hkernel_fn tfn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -340,7 +341,7 @@ int configure(mmz_env* h, int G, int NVP) {
 
 extern "C" {
 
-int mmz_abi_version(void) { return 3; }
+int mmz_abi_version(void) { return 4; }
 const char* mmz_last_error(void) { return g_err; }
 
 int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, uint32_t flags, mmz_handle* out) {
@@ -444,6 +445,15 @@ int mmz_kernel_config(mmz_handle h, int* lanes_per_env, int* threads_per_block, 
   if (envs_per_sm) *envs_per_sm = h->envs_per_sm;
   if (floats_per_env) *floats_per_env = h->L.stride;
   return MMZ_OK;
+}
+
+const char* mmz_kernel_name(mmz_handle h) {
+  if (!h) return "";
+  if (h->kname[0] == 0) {
+    if (h->use_t) snprintf(h->kname, sizeof h->kname, "maze_hkernel<%d>", h->NVP);
+    else snprintf(h->kname, sizeof h->kname, "maze_kernel<%d,%d,%d>", h->G, h->NVP, h->feat);
+  }
+  return h->kname;
 }
 
 int mmz_set_step_diag(mmz_handle h, int32_t* d_diag) {

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_PKG_ROOT, os.environ.get("MMZ_LIB", "libmmz.so"))
 MMZ_DONE, MMZ_TRUNCATED, MMZ_UNSTABLE = 1, 2, 4
 MMZ_AUTO_RESET = 1
 LAYOUT_ENV_MAJOR, LAYOUT_SOA = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib = None
 
@@ -47,6 +47,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "mmz_create": ([vp, sz, i32, i32, u32, ctypes.POINTER(vp)], i32),
         "mmz_dims": ([vp, ip, ip, ip, ip, ip], i32),
         "mmz_kernel_config": ([vp, ip, ip, ip, ip, ip], i32),
+        "mmz_kernel_name": ([vp], ctypes.c_char_p),
         "mmz_set_env_offset": ([vp, i32], i32),
         "mmz_set_step_diag": ([vp, vp], i32),
         "mmz_reset": ([vp, vp, u64, vp, vp], i32),
@@ -72,7 +73,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = (
-    "mmz_create", "mmz_dims", "mmz_kernel_config", "mmz_set_env_offset", "mmz_set_step_diag", "mmz_reset", "mmz_step", "mmz_step_host", "mmz_observe", "mmz_get_state",
+    "mmz_create", "mmz_dims", "mmz_kernel_config", "mmz_kernel_name", "mmz_set_env_offset", "mmz_set_step_diag", "mmz_reset", "mmz_step", "mmz_step_host", "mmz_observe", "mmz_get_state",
     "mmz_set_state", "mmz_forward", "mmz_launch_count", "mmz_last_error", "mmz_destroy", "mmz_abi_version",
 )
 
@@ -109,6 +110,7 @@ class BatchedSim:
         self.kernel_config = dict(zip(
             ("lanes_per_env", "threads_per_block", "smem_bytes", "envs_per_sm", "floats_per_env"),
             (c.value for c in cfg)))
+        self.kernel_config["kernel"] = self.lib.mmz_kernel_name(self._h).decode()
         if env_offset:
             self._check(self.lib.mmz_set_env_offset(self._h, int(env_offset)))
         dev = self.device
