@@ -1,10 +1,10 @@
 // mmz_math.cuh - small fp32 vector / quaternion / spatial-algebra helpers (device).
 //
-// Spatial convention (same as the CPU oracle, oracle/mmz_oracle.c:171-173): everything is
-// expressed in world axes about the WORLD ORIGIN. Motion vectors are
-// [angular(3); linear velocity of the point at the origin(3)], force vectors are
-// [torque about the origin(3); force(3)]. A spatial inertia is 10 floats:
-// I[0..5] rotational about the origin (xx,yy,zz,xy,xz,yz), I[6..8] = m*com, I[9] = m.
+// Spatial convention: everything is expressed in world axes about one REFERENCE POINT near the robot (the
+// callers subtract it: translation invariant, and it avoids fp32 cancellation far from the maze origin).
+// Motion vectors are [angular(3); linear velocity of the point at the reference(3)], force vectors are
+// [torque about the reference(3); force(3)]. A spatial inertia is 10 floats:
+// I[0..5] rotational about the reference (xx,yy,zz,xy,xz,yz), I[6..8] = m*com, I[9] = m.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -1,0 +1,146 @@
+"""CPU-side checks of the drop-in boundary (no GPU, no compute calls into libmmz):
+  * libmmz.so loads and exports every function include/mmz.h declares, with the ABI version the binding expects;
+  * error behaviour that does not need a device: NULL / bad arguments return negative codes and set mmz_last_error;
+  * the product path fails loudly without CUDA (no CPU fallback) and never imports oracle/;
+  * the host-side mirror of the reference's interface: registered ids, spaces, custom MazeTask recipe (README.md:79-127).
+"""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+PKG = os.path.join(ROOT, "mujoco-maze_b200")
+
+
+def _lib_path():
+    p = os.path.join(PKG, "libmmz.so")
+    if not os.path.exists(p):
+        sys.path.insert(0, PKG)
+        import build_native
+
+        build_native.build(verbose=False)
+    return p
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "mmz.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mmz_[a-z_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_functions()
+    assert len(names) >= 16 and "mmz_step" in names and "mmz_step_host" in names
+    lib = ctypes.CDLL(_lib_path())
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"include/mmz.h declares {missing} but libmmz.so does not export them"
+    # and the Python binding declares a signature for every one of them
+    from mujoco_maze import backend
+
+    assert sorted(backend.EXPORTED_SYMBOLS) == names
+    lib2 = backend.load_library(_lib_path())
+    assert lib2.mmz_abi_version() == backend.ABI_VERSION
+
+
+def test_model_header_matches_python_layout():
+    """include/mmz_model.h is generated from model_layout.py: sizes must agree with the blob the compiler emits."""
+    from conftest import make_model
+
+    hdr = open(os.path.join(ROOT, "include", "mmz_model.h")).read()
+    nint = int(re.search(r"#define MMZ_MODEL_NINT (\d+)", hdr).group(1))
+    nreal = int(re.search(r"#define MMZ_MODEL_NREAL (\d+)", hdr).group(1))
+    model = make_model("AntUMaze-v0")
+    assert len(model.blob(4)) == 4 * nint + 4 * nreal
+    assert len(model.blob(8)) == 4 * nint + 8 * nreal
+
+
+def test_bad_arguments_return_error_codes_without_a_device():
+    from mujoco_maze import backend
+
+    lib = backend.load_library(_lib_path())
+    h = ctypes.c_void_p()
+    assert lib.mmz_create(None, 0, 4, 0, 0, ctypes.byref(h)) == -1  # MMZ_ERR_INVALID
+    assert b"null" in lib.mmz_last_error()
+    blob = b"\0" * 16
+    assert lib.mmz_create(blob, len(blob), 4, 0, 0, ctypes.byref(h)) == -2  # MMZ_ERR_MODEL: wrong size
+    assert b"bytes" in lib.mmz_last_error()
+    assert lib.mmz_step(None, None, None, None, None, None, None) == -1
+    assert lib.mmz_dims(None, None, None, None, None, None) == -1
+    assert lib.mmz_launch_count(None) == 0
+    lib.mmz_destroy(None)  # no-op
+
+
+def test_no_cpu_fallback_and_no_oracle_import():
+    """Without CUDA the step path must raise; importing the package must not pull in oracle/."""
+    code = (
+        "import sys; sys.path[:0] = [%r, %r]\n"
+        "import mujoco_maze\n"
+        "from mujoco_maze import gym\n"
+        "from mujoco_maze.backend import MmzError\n"
+        "env = gym.make('PointUMaze-v0')\n"
+        "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'product imported oracle/'\n"
+        "import torch\n"
+        "if torch.cuda.is_available():\n"
+        "    print('HAS_CUDA')\n"
+        "else:\n"
+        "    try:\n"
+        "        env.reset()\n"
+        "    except MmzError as e:\n"
+        "        print('RAISED', e)\n"
+        "    else:\n"
+        "        raise SystemExit('reset() ran without CUDA: there must be no CPU fallback')\n"
+    ) % (PKG, ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "RAISED" in out.stdout or "HAS_CUDA" in out.stdout
+    for root, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports oracle/"
+                assert "mmz_oracle" not in text, f"{f} references the oracle"
+
+
+def test_registered_ids_spaces_and_custom_task():
+    import mujoco_maze  # noqa: F401
+    from mujoco_maze import gym
+    from mujoco_maze.maze_env_utils import MazeCell
+    from mujoco_maze.maze_task import MazeGoal, MazeTask
+    from mujoco_maze.point import PointEnv
+
+    ids = [s for s in gym.registry_ids()] if hasattr(gym, "registry_ids") else None
+    env = gym.make("AntUMaze-v0").unwrapped
+    assert env.observation_space.shape == (30,) and env.action_space.shape == (8,)
+    assert np.allclose(env.action_space.high, 30.0)
+    p = gym.make("PointUMaze-v1").unwrapped
+    assert p.observation_space.shape == (7,) and np.allclose(p.action_space.high, [1.0, 0.25])
+    if ids is not None:
+        assert "Ant4Rooms-v0" in ids and "PointUMaze-v0" in ids
+
+    # README.md:79-127: a user-defined task registers and compiles (host-side reward falls back to Python)
+    class GoalRewardEMaze(MazeTask):
+        REWARD_THRESHOLD = 0.9
+        PENALTY = -0.0001
+
+        def __init__(self, scale):
+            super().__init__(scale)
+            self.goals = [MazeGoal(np.array([0.0, 4.0]) * scale)]
+
+        def reward(self, obs):
+            return 1.0 if self.termination(obs) else self.PENALTY
+
+        @staticmethod
+        def create_maze():
+            E, B, R = MazeCell.EMPTY, MazeCell.BLOCK, MazeCell.ROBOT
+            return [[B, B, B, B, B], [B, R, E, E, B], [B, B, B, E, B], [B, E, E, E, B], [B, B, B, B, B]]
+
+    gym.register(id="PointEMaze-vtest", entry_point="mujoco_maze.maze_env:MazeEnv",
+                 kwargs=dict(model_cls=PointEnv, maze_task=GoalRewardEMaze, maze_size_scaling=4.0, inner_reward_scaling=0.0))
+    e = gym.make("PointEMaze-vtest").unwrapped
+    assert e.model.nseg > 0 and e.observation_space.shape == (7,)
