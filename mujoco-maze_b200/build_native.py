@@ -56,11 +56,11 @@ def build(force: bool = False, verbose: bool = True) -> str:
         if force or _stale(o, hdrs + [os.path.join(CSRC, "mmz_inst.cu")]):
             jobs.append(([nvcc, *NVCC_FLAGS, f"-DMMZ_G={g}", f"-DMMZ_NVP={nvp}", f"-DMMZ_FEAT={feat}", "-c",
                           os.path.join(CSRC, "mmz_inst.cu"), "-o", o], o + ".log"))
-    for nvp in (14, 16):
+    for nvp, box in ((14, 0), (16, 1)):
         h_o = os.path.join(OBJ, f"mmz_hinst_{nvp}.o")
         objs.append(h_o)
         if force or _stale(h_o, hdrs + [os.path.join(CSRC, "mmz_hinst.cu")]):
-            jobs.append(([nvcc, *NVCC_FLAGS, f"-DMMZ_NVP={nvp}", "-c", os.path.join(CSRC, "mmz_hinst.cu"), "-o", h_o], h_o + ".log"))
+            jobs.append(([nvcc, *NVCC_FLAGS, f"-DMMZ_NVP={nvp}", f"-DMMZ_BOX={box}", "-c", os.path.join(CSRC, "mmz_hinst.cu"), "-o", h_o], h_o + ".log"))
     if jobs:
         if verbose:
             print(f"[build_native] compiling {len(jobs)} translation unit(s) for sm_100a ...", flush=True)

@@ -208,14 +208,21 @@ bool configure_h(mmz_env* h, int* rc) {
   if (m.step_kind != MMZ_STEP_TORQUE || m.manual_collision) return false;
   if (m.density > 0.f || m.viscosity > 0.f) return false;
   if (m.nv < 9 || m.nv > 16) return false;  // small models are already served well by 8 lanes per environment
+  int nbox = 0;
   for (int g = 0; g < m.ngeom; g++) {
-    if (m.geom_type[g] != MMZ_GEOM_SPHERE && m.geom_type[g] != MMZ_GEOM_CAPSULE) return false;
-    for (int g2 = g + 1; g2 < m.ngeom; g2++) {  // no moving-moving pair may pass the contact filter
+    const int t = m.geom_type[g];
+    if (t != MMZ_GEOM_SPHERE && t != MMZ_GEOM_CAPSULE && t != MMZ_GEOM_BOX) return false;
+    nbox += t == MMZ_GEOM_BOX;
+    for (int g2 = g + 1; g2 < m.ngeom; g2++) {  // a moving-moving pair that passes the contact filter must involve a box
       const int b1 = m.geom_body[g], b2 = m.geom_body[g2];
       if (b1 == b2 || m.body_parent[b1] == b2 || m.body_parent[b2] == b1) continue;
-      if ((m.geom_contype[g] & m.geom_conaffinity[g2]) || (m.geom_contype[g2] & m.geom_conaffinity[g])) return false;
+      const bool pair = (m.geom_contype[g] & m.geom_conaffinity[g2]) || (m.geom_contype[g2] & m.geom_conaffinity[g]);
+      if (pair && t != MMZ_GEOM_BOX && m.geom_type[g2] != MMZ_GEOM_BOX) return false;
     }
   }
+  const bool box = nbox > 0;
+  if (box && m.nv <= 14) return false;   // instances built: <14, no boxes> and <16, boxes>
+  if (!box && m.nv > 14) return false;
   TLayout L;
   memset(&L, 0, sizeof L);
   L.nb = m.nbody; L.nj = m.njnt; L.nv = m.nv; L.nq = m.nq; L.nu = m.nu; L.ng = m.ngeom; L.nobj = m.nobj; L.obs_dim = m.obs_dim;
@@ -225,40 +232,47 @@ bool configure_h(mmz_env* h, int* rc) {
   L.nlev = nlev; L.ldm = m.nv + 1;
   L.cstride = C_STRIDE;
   L.nstate = m.nq + 2 * m.nv + 3 * m.nobj;
+  const int nitems = L.ng + nbox * (1 + 2 * 9 + (nbox - 1));  // HEnv::n_items
   int o = 0;
   auto take = [&](int n) { int r = o; o += n; return r; };
   L.o_cnt = take(TN_CNT);
   L.o_qpos = take(L.nq); L.o_qvel = take(L.nv); L.o_qacc = take(L.nv); L.o_objpos = take(3 * L.nobj > 0 ? 3 * L.nobj : 1);
   L.o_ctrl = take(L.nu > 0 ? L.nu : 1); L.o_act = take(L.nu > 0 ? L.nu : 1);
   L.o_q0 = take(L.nq); L.o_v0 = take(L.nv); L.o_accv = take(L.nv); L.o_acca = take(L.nv);
-  L.o_xpos = take(3 * L.nb); L.o_xquat = take(4 * L.nb); L.o_xmat = take(9 * L.nb);
-  L.o_gpos = take(3 * L.ng); L.o_gax = take(3 * L.ng);
+  L.o_xpos = take(3 * L.nb);
+  L.o_gpos = take(3 * L.ng); L.o_gax = take(3 * L.ng); L.o_gmat = take(nbox > 0 ? 9 * nbox : 1);
   L.o_cdof = take(6 * L.nv);
-  L.o_iw = take(10 * L.nb); L.o_vel = take(6 * L.nb);
-  L.o_ic = take(10 * L.nb); L.o_acc = take(6 * L.nb); L.o_frc = take(6 * L.nb); L.o_fsub = take(6 * L.nb);
+  L.o_vel = take(6 * L.nb);
   L.o_M = take(L.nv * L.ldm);
   L.o_smooth = take(L.nv); L.o_dir = take(L.nv);
-  L.o_gcnt = take(L.ng > 0 ? L.ng : 1); L.o_obs = take(L.obs_dim);
+  L.o_gcnt = take(nitems); L.o_obs = take(L.obs_dim);
+  // Last: the arrays that are dead once the mass matrix and the smooth forces exist (orientations, inertias, bias
+  // accelerations and forces). The contact slots are written after that point and OVERLAY them, then run on.
+  const int dead0 = o;
+  L.o_xquat = take(4 * L.nb); L.o_xmat = take(9 * L.nb); L.o_iw = take(10 * L.nb);
+  L.o_ic = take(10 * L.nb); L.o_acc = take(6 * L.nb); L.o_frc = take(6 * L.nb); L.o_fsub = take(6 * L.nb);
+  const int dead1 = o;
   L.model_bytes = round_up(round_up((int)sizeof(mmz_model), 16) + (int)sizeof(TDerived), 16);
   int dev_smem = 0;
   if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess) return false;
   const int avail = (dev_smem - round_up(L.model_bytes, 128) - 256) / (HS * 4);  // slots per environment
-  int maxcon = (avail - o) / L.cstride;
-  if (maxcon > 24) maxcon = 24;
-  if (maxcon < 12) return false;  // does not fit: use the lanes-per-environment kernel
+  if (avail < dead1) return false;
+  int maxcon = (avail - dead0) / L.cstride;
+  const int want = box ? std::min(40, 16 + 8 * nbox) : 24;
+  if (maxcon > want) maxcon = want;
+  if (maxcon < (box ? 24 : 16)) return false;  // does not fit: use the lanes-per-environment kernel
   L.maxcon = maxcon;
-  L.o_con = take(maxcon * L.cstride);
-  L.nslots = o;
+  L.o_con = dead0;
+  L.nslots = std::max(dead1, dead0 + maxcon * L.cstride);
   h->TL = L;
   h->smem_bytes = round_up(L.model_bytes, 128) + L.nslots * HS * 4;
   for (int mode = 0; mode < 5; mode++) {
-    h->tfn[mode] = m.nv <= 14 ? mmz::get_hkernel_14(mode) : mmz::get_hkernel_16(mode);
+    h->tfn[mode] = box ? mmz::get_hkernel_16(mode) : mmz::get_hkernel_14(mode);
     cudaError_t e = cudaFuncSetAttribute(h->tfn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
     if (e != cudaSuccess) { *rc = fail(MMZ_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return false; }
   }
   h->use_t = true;
-  if (const char* e = getenv("MMZ_TOL")) h->tol = (float)atof(e);  // development aid
-  h->G = 16; h->NVP = m.nv <= 14 ? 14 : 16; h->tpb = TW * 32; h->envs_per_sm = TE;
+  h->G = 16; h->NVP = box ? 16 : 14; h->feat = box ? FEAT_BOX : 0; h->tpb = TW * 32; h->envs_per_sm = TE;
   h->L.stride = L.nslots; h->L.nstate = L.nstate; h->L.model_bytes = L.model_bytes;
   return true;
 }
@@ -281,6 +295,9 @@ void make_tderived(const mmz_model& m, TDerived* d) {
   }
   d->lvl_off[nlev] = k;
   d->ident[0] = d->ident[4] = d->ident[8] = 1.f;
+  for (int g = 0; g < MMZ_MAXGEOM; g++) d->boxord[g] = -1;
+  for (int g = 0; g < m.ngeom; g++)
+    if (m.geom_type[g] == MMZ_GEOM_BOX) { d->boxord[g] = d->nboxg; d->boxg[d->nboxg++] = g; }
 }
 
 int configure(mmz_env* h, int G, int NVP) {
@@ -450,7 +467,7 @@ int mmz_kernel_config(mmz_handle h, int* lanes_per_env, int* threads_per_block, 
 const char* mmz_kernel_name(mmz_handle h) {
   if (!h) return "";
   if (h->kname[0] == 0) {
-    if (h->use_t) snprintf(h->kname, sizeof h->kname, "maze_hkernel<%d>", h->NVP);
+    if (h->use_t) snprintf(h->kname, sizeof h->kname, "maze_hkernel<%d,%d>", h->NVP, h->feat);
     else snprintf(h->kname, sizeof h->kname, "maze_kernel<%d,%d,%d>", h->G, h->NVP, h->feat);
   }
   return h->kname;

@@ -41,8 +41,11 @@ struct TDerived {               // appended to the model blob in device memory
   int32_t anc[MMZ_MAXBODY];     // bit a set in anc[b]: body a is b or an ancestor of b
   int32_t lvl_off[MMZ_MAXBODY + 1];  // bodies of level l: lvl_body[lvl_off[l] .. lvl_off[l+1])
   int32_t lvl_body[MMZ_MAXBODY];
+  int32_t boxg[MMZ_MAXGEOM];    // geoms of type box on moving bodies, in geom order
+  int32_t boxord[MMZ_MAXGEOM];  // geom -> its index in boxg (or -1)
+  int32_t nboxg;
   int32_t nlev;
-  int32_t pad[3];
+  int32_t pad[2];
   float ident[9];
   float padf[3];
 };
@@ -52,7 +55,7 @@ struct TLayout {
   int maxcon, cstride, ldm, nstate, nslots, model_bytes;
   int o_qpos, o_qvel, o_qacc, o_objpos;  // persisted rows, in this order
   int o_ctrl, o_q0, o_v0, o_accv, o_acca;
-  int o_xpos, o_xquat, o_xmat, o_gpos, o_gax, o_cdof;
+  int o_xpos, o_xquat, o_xmat, o_gpos, o_gax, o_gmat, o_cdof;
   int o_iw, o_ic, o_vel, o_acc, o_frc, o_fsub;
   int o_M, o_smooth, o_dir;
   int o_con, o_cnt, o_gcnt, o_obs, o_act;
@@ -81,7 +84,7 @@ struct TArgs {
 
 constexpr int HS = 33;  // row stride of the [slot][33] workspace
 
-template <int NVP>
+template <int NVP, int BOX>
 struct HEnv {
   const mmz_model* m;
   const TDerived* dv;
@@ -279,6 +282,15 @@ struct HEnv {
     mat_vec(ax, Rb, az);
 #pragma unroll
     for (int k = 0; k < 3; k++) { S(L.o_gpos + 3 * g + k) = p[k] + S(L.o_xpos + 3 * b + k); S(L.o_gax + 3 * g + k) = ax[k]; }
+    if (BOX && dv->boxord[g] >= 0) {  // box geoms need their whole frame
+      float R[9];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) R[3 * r + c] = Rb[3 * r] * Rg[c] + Rb[3 * r + 1] * Rg[3 + c] + Rb[3 * r + 2] * Rg[6 + c];
+#pragma unroll
+      for (int k = 0; k < 9; k++) S(L.o_gmat + 9 * dv->boxord[g] + k) = R[k];
+    }
   }
   // sum over the subtree rooted at b of n-float records
   MMZ_DI void subtree_sum(const TLayout& L, int b, int src, int dst, int n) {
@@ -331,10 +343,13 @@ struct HEnv {
     S(L.o_smooth + d) = passive - bias + act;
   }
 
-  MMZ_DI void mix_params(int g, bool floor, float* par /* margin, mu, solref[2], solimp[5] */) const {
-    const float om = floor ? m->floor_margin : m->wall_margin, of = floor ? m->floor_friction[0] : m->wall_friction[0];
-    const float* osr = floor ? m->floor_solref : m->wall_solref;
-    const float* osi = floor ? m->floor_solimp : m->wall_solimp;
+  // mixed contact parameters of geom g against `other` (-1 floor, -2 wall / platform box, >= 0 another geom)
+  MMZ_DI void mix_params(int g, int other, float* par /* margin, mu, solref[2], solimp[5] */) const {
+    float om, of;
+    const float *osr, *osi;
+    if (other == -1) { om = m->floor_margin; of = m->floor_friction[0]; osr = m->floor_solref; osi = m->floor_solimp; }
+    else if (other == -2) { om = m->wall_margin; of = m->wall_friction[0]; osr = m->wall_solref; osi = m->wall_solimp; }
+    else { om = m->geom_margin[other]; of = m->geom_friction[other][0]; osr = m->geom_solref[other]; osi = m->geom_solimp[other]; }
     par[0] = fmaxf(m->geom_margin[g], om);
     par[1] = fmaxf(m->geom_friction[g][0], of);
 #pragma unroll
@@ -349,11 +364,17 @@ struct HEnv {
     *i0 = max(0, (int)ceilf((c[1] - ext[1] + m->origin[1] - hs) / s));
     *i1 = min(m->grid_h - 1, (int)floorf((c[1] + ext[1] + m->origin[1] + hs) / s));
   }
-  // stores a narrow-phase record into contact slot `slot` (layout C_* of mmz_layout.h)
-  MMZ_DI void write_contact(const TLayout& L, int slot, const RawContact& rc, int body, float sign, int g, bool floor) {
+  MMZ_DI bool moving_pair_ok(int g1, int g2) const {
+    const int b1 = m->geom_body[g1], b2 = m->geom_body[g2];
+    if (b1 == b2 || m->body_parent[b1] == b2 || m->body_parent[b2] == b1) return false;
+    return (m->geom_contype[g1] & m->geom_conaffinity[g2]) || (m->geom_contype[g2] & m->geom_conaffinity[g1]);
+  }
+  // stores a narrow-phase record into contact slot `slot` (layout C_* of mmz_layout.h); the normal points
+  // from body b1 (geom1) to body b2 (geom2), -1 = world
+  __device__ __noinline__ void write_contact(const TLayout& L, int slot, const RawContact& rc, int b1, int b2, float iw, int g, int other) {
     const int o = L.o_con + slot * L.cstride;
     float fr[9], par[9];
-    mix_params(g, floor, par);
+    mix_params(g, other, par);
 #pragma unroll
     for (int k = 0; k < 3; k++) { fr[k] = rc.normal[k]; fr[3 + k] = rc.hint[k]; }
     make_frame(fr);
@@ -366,90 +387,186 @@ struct HEnv {
     S(o + C_MU) = par[1];
 #pragma unroll
     for (int k = 0; k < 7; k++) S(o + C_SOLREF + k) = par[2 + k];
-    S(o + C_INVW) = m->geom_invweight[g];
-    // geom1 -> geom2: the floor plane is geom1 of its pairs, a maze box is geom2
-    S(o + C_BODY1) = __int_as_float(sign > 0.f ? -1 : body);
-    S(o + C_BODY2) = __int_as_float(sign > 0.f ? body : -1);
+    S(o + C_INVW) = iw;
+    S(o + C_BODY1) = __int_as_float(b1);
+    S(o + C_BODY2) = __int_as_float(b2);
   }
-  // Contacts of sphere / capsule geom g against the floor plane and the maze boxes near it. pass 0 counts
-  // (into o_gcnt), pass 1 writes them at the slots following those of the geoms before it: the order is
-  // (geom, floor first, then cells row-major, wall before platform), independent of warp timing.
-  MMZ_DI void geom_contacts(const TLayout& L, int g, int pass) {
-    const int type = m->geom_type[g];
-    const bool capsule = type == MMZ_GEOM_CAPSULE;
-    int n = 0, base = 0;
-    if (pass == 1) {
+  // number of collision items: one per geom, then (BOX only) BCAND candidate slots per box geom
+  static constexpr int BCELLS = 9;                       // maze cells a box geom can reach (3 x 3)
+  MMZ_DI int box_cands() const { return 1 + 2 * BCELLS + (dv->nboxg - 1); }  // floor, cells x {wall, platform}, other boxes
+  MMZ_DI int n_items(const TLayout& L) const { return L.ng + (BOX ? dv->nboxg * box_cands() : 0); }
+  MMZ_DI int item_base(const TLayout& L, int item) const {
+    int base = 0;
 #pragma unroll 1
-      for (int gg = 0; gg < g; gg++) base += I(L.o_gcnt + gg);
-    }
-    const bool valid = (type == MMZ_GEOM_SPHERE || capsule) && ((m->geom_contype[g] | m->geom_conaffinity[g]) & 1) && m->collision_on;
-    if (valid) {
-      const float r = m->geom_size[g][0], gmarg = m->geom_margin[g];
-      const int body = m->geom_body[g];
-      float gp[3], axv[3], p0[3], p1[3], ext[3];
+    for (int k = 0; k < item; k++) base += I(L.o_gcnt + k);
+    return base;
+  }
+  // Collision item `item`. pass 0 counts its contacts (into o_gcnt), pass 1 writes them at the slots following those
+  // of the items before it: the contact order is the item order, independent of warp timing.
+  //   item < ng: sphere / capsule geom against the floor plane, the maze boxes near it and the movable box geoms;
+  //   item >= ng (BOX): candidate c of box geom k: the floor (plane-box corners), a maze box or a later box geom (box-box).
+  MMZ_DI void collide_item(const TLayout& L, int item, int pass) {
+    int n = 0;
+    const int base = pass == 1 ? item_base(L, item) : 0;
+    if (item < L.ng) {
+      const int g = item, type = m->geom_type[g];
+      const bool capsule = type == MMZ_GEOM_CAPSULE;
+      const bool valid = (type == MMZ_GEOM_SPHERE || capsule) && ((m->geom_contype[g] | m->geom_conaffinity[g]) & 1) && m->collision_on;
+      if (valid) {
+        const float r = m->geom_size[g][0], gmarg = m->geom_margin[g], invw = m->geom_invweight[g];
+        const int body = m->geom_body[g];
+        float gp[3], axv[3], p0[3], p1[3], ext[3];
 #pragma unroll
-      for (int k = 0; k < 3; k++) { gp[k] = S(L.o_gpos + 3 * g + k); axv[k] = S(L.o_gax + 3 * g + k); }
-      const float hl = capsule ? m->geom_size[g][1] : 0.f;
+        for (int k = 0; k < 3; k++) { gp[k] = S(L.o_gpos + 3 * g + k); axv[k] = S(L.o_gax + 3 * g + k); }
+        const float hl = capsule ? m->geom_size[g][1] : 0.f;
 #pragma unroll
-      for (int k = 0; k < 3; k++) { const float a = axv[k] * hl; p0[k] = gp[k] + a; p1[k] = gp[k] - a; ext[k] = fabsf(a); }
-      // ---- floor plane (normal +z); geom1 = plane, geom2 = this geom
-      if (m->has_floor) {
-        const float margin = fmaxf(gmarg, m->floor_margin);
-        const float d0 = p0[2] - m->floor_z - r, d1 = p1[2] - m->floor_z - r;
-        float hint[3] = {0.f, 0.f, 0.f};
-        if (capsule && fabsf(axv[2]) <= 0.999999f) { hint[0] = axv[0]; hint[1] = axv[1]; hint[2] = axv[2]; }  // first tangent along the axis
+        for (int k = 0; k < 3; k++) { const float a = axv[k] * hl; p0[k] = gp[k] + a; p1[k] = gp[k] - a; ext[k] = fabsf(a); }
+        // ---- floor plane (normal +z); geom1 = plane, geom2 = this geom
+        if (m->has_floor) {
+          const float margin = fmaxf(gmarg, m->floor_margin);
+          const float d0 = p0[2] - m->floor_z - r, d1 = p1[2] - m->floor_z - r;
+          float hint[3] = {0.f, 0.f, 0.f};
+          if (capsule && fabsf(axv[2]) <= 0.999999f) { hint[0] = axv[0]; hint[1] = axv[1]; hint[2] = axv[2]; }  // first tangent along the axis
 #pragma unroll 1
-        for (int end = 0; end < 2; end++) {
-          const float d = end == 0 ? d0 : d1;
-          if ((end == 1 && !capsule) || !(d < margin)) continue;
-          if (pass == 1 && base + n < L.maxcon) {
-            RawContact rc;
+          for (int end = 0; end < 2; end++) {
+            const float d = end == 0 ? d0 : d1;
+            if ((end == 1 && !capsule) || !(d < margin)) continue;
+            if (pass == 1 && base + n < L.maxcon) {
+              RawContact rc;
 #pragma unroll
-            for (int k = 0; k < 3; k++) { rc.pos[k] = end == 0 ? p0[k] : p1[k]; rc.normal[k] = (k == 2) ? 1.f : 0.f; rc.hint[k] = hint[k]; }
-            rc.dist = d; rc.pos[2] -= r + 0.5f * d;
-            write_contact(L, base + n, rc, body, 1.f, g, true);
+              for (int k = 0; k < 3; k++) { rc.pos[k] = end == 0 ? p0[k] : p1[k]; rc.normal[k] = (k == 2) ? 1.f : 0.f; rc.hint[k] = hint[k]; }
+              rc.dist = d; rc.pos[2] -= r + 0.5f * d;
+              write_contact(L, base + n, rc, -1, body, invw, g, -1);
+            }
+            n++;
           }
-          n++;
+        }
+        // ---- box-shaped obstacles; geom1 = this geom, geom2 = box (the normal points from the geom into the box):
+        // the maze boxes of the cells it can reach (wall, then platform), then the movable box geoms
+        const float mg = r + fmaxf(gmarg, m->wall_margin);
+        ext[0] += mg; ext[1] += mg;
+        int i0, i1, j0, j1;
+        cell_range(gp, ext, &i0, &i1, &j0, &j1);
+        const int nslot = m->elevated ? 2 : 1, nj = max(0, j1 - j0 + 1), ncell = nj * max(0, i1 - i0 + 1);
+        const int ncand = nslot * ncell + (BOX ? dv->nboxg : 0);
+#pragma unroll 1
+        for (int cand = 0; cand < ncand; cand++) {
+          float bc[3], bR[9], bh[3], margin, iw = invw;
+          int other = -2, b2 = -1;
+          if (cand < nslot * ncell) {
+            const int ci = cand / nslot, slot = cand - ci * nslot, i = i0 + ci / nj, j = j0 + ci % nj;
+            const int code = m->grid[i * m->grid_w + j];
+            if (!(code & (slot == 0 ? MMZ_CELL_WALL : MMZ_CELL_PLATFORM))) continue;
+            bc[0] = j * m->cell_size - m->origin[0]; bc[1] = i * m->cell_size - m->origin[1]; bc[2] = slot == 0 ? m->wall_z : m->plat_z;
+#pragma unroll
+            for (int k = 0; k < 9; k++) bR[k] = dv->ident[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) bh[k] = m->wall_half[k];
+            margin = fmaxf(gmarg, m->wall_margin);
+          } else {
+            const int kb = cand - nslot * ncell, gb = dv->boxg[kb];
+            if (!moving_pair_ok(g, gb)) continue;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { bc[k] = S(L.o_gpos + 3 * gb + k); bh[k] = m->geom_size[gb][k]; }
+#pragma unroll
+            for (int k = 0; k < 9; k++) bR[k] = S(L.o_gmat + 9 * kb + k);
+            margin = fmaxf(gmarg, m->geom_margin[gb]);
+            other = gb; b2 = m->geom_body[gb];
+            iw = invw + m->geom_invweight[gb];
+          }
+          // capsule: both end caps when both are within the margin, otherwise the segment point nearest the box
+          RawContact r0, r1;
+          int n0 = sphere_box(p0, r, bc, bR, bh, margin, &r0), n1 = 0;
+          if (capsule) {
+            n1 = sphere_box(p1, r, bc, bR, bh, margin, &r1);
+            if (!(n0 && n1)) {
+              const float ts = capsule_nearest(p0, p1, bc, bR, bh);
+              float pt[3];
+#pragma unroll
+              for (int k = 0; k < 3; k++) pt[k] = p0[k] + ts * (p1[k] - p0[k]);
+              n0 = sphere_box(pt, r, bc, bR, bh, margin, &r0);
+              n1 = 0;
+            }
+          }
+          if (n0) { if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r0, body, b2, iw, g, other); n++; }
+          if (n1) { if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r1, body, b2, iw, g, other); n++; }
         }
       }
-      // ---- maze boxes; geom1 = this geom, geom2 = box (normal points from the geom into the box)
-      const float mg = r + fmaxf(gmarg, m->wall_margin);
-      ext[0] += mg; ext[1] += mg;
-      int i0, i1, j0, j1;
-      cell_range(gp, ext, &i0, &i1, &j0, &j1);
-      const int nslot = m->elevated ? 2 : 1;
-      const float margin = fmaxf(gmarg, m->wall_margin);
-#pragma unroll 1
-      for (int i = i0; i <= i1; i++)
-#pragma unroll 1
-        for (int j = j0; j <= j1; j++) {
-          const int code = m->grid[i * m->grid_w + j];
-#pragma unroll 1
-          for (int slot = 0; slot < nslot; slot++) {
-            if (!(code & (slot == 0 ? MMZ_CELL_WALL : MMZ_CELL_PLATFORM))) continue;
-            const float bc[3] = {j * m->cell_size - m->origin[0], i * m->cell_size - m->origin[1], slot == 0 ? m->wall_z : m->plat_z};
-            // capsule: both end caps when both are within the margin, otherwise the segment point nearest the box
-            RawContact r0, r1;
-            int n0 = sphere_box(p0, r, bc, dv->ident, m->wall_half, margin, &r0), n1 = 0;
-            if (capsule) {
-              n1 = sphere_box(p1, r, bc, dv->ident, m->wall_half, margin, &r1);
-              if (!(n0 && n1)) {
-                const float ts = capsule_nearest(p0, p1, bc, dv->ident, m->wall_half);
-                float pt[3];
+    } else if (BOX) {
+      const int bc_n = box_cands(), kbox = (item - L.ng) / bc_n, cand = (item - L.ng) - kbox * bc_n;
+      const int g = dv->boxg[kbox];
+      if (((m->geom_contype[g] | m->geom_conaffinity[g]) & 1) && m->collision_on) {
+        const int body = m->geom_body[g];
+        const float invw = m->geom_invweight[g];
+        float gp[3], gm[9], sz[3];
 #pragma unroll
-                for (int k = 0; k < 3; k++) pt[k] = p0[k] + ts * (p1[k] - p0[k]);
-                n0 = sphere_box(pt, r, bc, dv->ident, m->wall_half, margin, &r0);
-                n1 = 0;
+        for (int k = 0; k < 3; k++) { gp[k] = S(L.o_gpos + 3 * g + k); sz[k] = m->geom_size[g][k]; }
+#pragma unroll
+        for (int k = 0; k < 9; k++) gm[k] = S(L.o_gmat + 9 * kbox + k);
+        RawContact rc[8];
+        int b1 = -1, b2 = body, other = -1;
+        float iw = invw;
+        if (cand == 0) {  // corners below the plane, at most 4; geom1 = plane
+          if (m->has_floor) {
+            const float margin = fmaxf(m->geom_margin[g], m->floor_margin);
+            for (int c = 0; c < 8 && n < 4; c++) {
+              float loc[3] = {(c & 1 ? 1.f : -1.f) * sz[0], (c & 2 ? 1.f : -1.f) * sz[1], (c & 4 ? 1.f : -1.f) * sz[2]}, wp[3];
+              mat_vec(wp, gm, loc);
+              const float dist = wp[2] + gp[2] - m->floor_z;
+              if (dist < margin) {
+                rc[n].dist = dist;
+                rc[n].pos[0] = wp[0] + gp[0]; rc[n].pos[1] = wp[1] + gp[1]; rc[n].pos[2] = wp[2] + gp[2] - 0.5f * dist;
+                rc[n].normal[0] = 0.f; rc[n].normal[1] = 0.f; rc[n].normal[2] = 1.f;
+                rc[n].hint[0] = rc[n].hint[1] = rc[n].hint[2] = 0.f;
+                n++;
               }
             }
-            if (n0) { if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r0, body, -1.f, g, false); n++; }
-            if (n1) { if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r1, body, -1.f, g, false); n++; }
+          }
+        } else if (cand - 1 < 2 * BCELLS) {  // maze boxes; geom1 = wall (lower geom id), geom2 = this box
+          const float wallmargin = fmaxf(m->geom_margin[g], m->wall_margin);
+          float ext[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) ext[k] = fabsf(gm[3 * k]) * sz[0] + fabsf(gm[3 * k + 1]) * sz[1] + fabsf(gm[3 * k + 2]) * sz[2];
+          ext[0] += wallmargin; ext[1] += wallmargin;
+          int i0, i1, j0, j1;
+          cell_range(gp, ext, &i0, &i1, &j0, &j1);
+          const int nj = max(0, j1 - j0 + 1), ncell = nj * max(0, i1 - i0 + 1);
+          const int ci = (cand - 1) >> 1, slot = (cand - 1) & 1;
+          if (ci < ncell) {
+            const int i = i0 + ci / nj, j = j0 + ci % nj;
+            const int code = m->grid[i * m->grid_w + j];
+            if (code & (slot == 0 ? MMZ_CELL_WALL : MMZ_CELL_PLATFORM)) {
+              const float bc[3] = {j * m->cell_size - m->origin[0], i * m->cell_size - m->origin[1], slot == 0 ? m->wall_z : m->plat_z};
+              other = -2;
+              n = box_box(bc, dv->ident, m->wall_half, gp, gm, sz, wallmargin, rc);
+            }
+          }
+          if (cand == 1 && ncell > BCELLS && pass == 0) I(L.o_cnt + TN_OVERFLOW) = 1;  // the box reaches more cells than slots
+        } else {  // box against a later box geom on another moving body
+          const int k2 = kbox + 1 + (cand - 1 - 2 * BCELLS);
+          if (k2 < dv->nboxg) {
+            const int g2 = dv->boxg[k2];
+            if (moving_pair_ok(g, g2)) {
+              float gp2[3], gm2[9];
+#pragma unroll
+              for (int k = 0; k < 3; k++) gp2[k] = S(L.o_gpos + 3 * g2 + k);
+#pragma unroll
+              for (int k = 0; k < 9; k++) gm2[k] = S(L.o_gmat + 9 * k2 + k);
+              other = g2; b1 = body; b2 = m->geom_body[g2];
+              iw = invw + m->geom_invweight[g2];
+              n = box_box(gp, gm, sz, gp2, gm2, m->geom_size[g2], fmaxf(m->geom_margin[g], m->geom_margin[g2]), rc);
+            }
           }
         }
+        if (pass == 1)
+          for (int k = 0; k < n; k++)
+            if (base + k < L.maxcon) write_contact(L, base + k, rc[k], b1, b2, iw, g, other);
+      }
     }
-    if (pass == 0) I(L.o_gcnt + g) = n;
+    if (pass == 0) I(L.o_gcnt + item) = n;
   }
 
+  // ------------------------------------------------------------------ constraint rows (mj_makeConstraint)
   MMZ_DI static float impedance(const float* si, float r) {
     const float d0 = fminf(fmaxf(si[0], 1e-4f), 0.9999f), d1 = fminf(fmaxf(si[1], 1e-4f), 0.9999f);
     const float width = si[2], mid = si[3], power = si[4];
@@ -767,6 +884,7 @@ struct HEnv {
       __syncthreads();
     }
     // B: geom poses, composite inertias, subtree forces
+    if (wid == TW - 1) I(L.o_cnt + TN_OVERFLOW) = 0;
     {
       const int nt = L.ng + 2 * L.nb;
       for (int t = wid; t < nt; t += TW) {
@@ -777,22 +895,23 @@ struct HEnv {
     }
     __syncthreads();
     // C: contact counting, mass matrix rows, smooth forces
+    const int nit = n_items(L);
     {
-      const int nt = 2 * L.nv + L.ng;
+      const int nt = 2 * L.nv + nit;
       for (int t = wid; t < nt; t += TW) {
-        if (t < L.ng) geom_contacts(L, t, 0);
-        else if (t < L.ng + L.nv) mass_row(L, t - L.ng);
-        else smooth_dof(L, t - L.ng - L.nv);
+        if (t < nit) collide_item(L, t, 0);
+        else if (t < nit + L.nv) mass_row(L, t - nit);
+        else smooth_dof(L, t - nit - L.nv);
       }
     }
     __syncthreads();
-    // D: contacts into their slots
-    for (int g = wid; g < L.ng; g += TW) geom_contacts(L, g, 1);
+    // D: contacts into their slots (over the slots of arrays that are dead by now, see the layout)
+    for (int t = wid; t < nit; t += TW) collide_item(L, t, 1);
     if (wid == TW - 1) {
       int n = 0;
 #pragma unroll 1
-      for (int g = 0; g < L.ng; g++) n += I(L.o_gcnt + g);
-      I(L.o_cnt + TN_OVERFLOW) = n > L.maxcon ? 1 : 0;
+      for (int k = 0; k < nit; k++) n += I(L.o_gcnt + k);
+      if (n > L.maxcon) I(L.o_cnt + TN_OVERFLOW) = 1;
       I(L.o_cnt + TN_CON) = min(n, L.maxcon);
     }
     __syncthreads();

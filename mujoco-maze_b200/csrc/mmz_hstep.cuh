@@ -1,6 +1,6 @@
 // mmz_hstep.cuh - MazeEnv.step / reset / observe around the hybrid dynamics (mmz_hkernel.cuh).
 //
-// One launch of maze_hkernel<NVP, TMODE_STEP> is one MazeEnv.step (reference maze_env.py:448-481) of N lock-step
+// One launch of maze_hkernel<NVP, BOX, TMODE_STEP> is one MazeEnv.step (reference maze_env.py:448-481) of N lock-step
 // environments for torque-driven agents (AntEnv.step ant.py:61-73, SwimmerEnv.step swimmer.py:37-47):
 // frame_skip x mj_step, _get_obs (maze_env.py:351-369), MazeTask.reward / termination (maze_task.py),
 // TimeLimit truncation (__init__.py:31) and the optional in-kernel auto-reset (reset_model, ant.py:84-96).
@@ -21,9 +21,9 @@ MMZ_DI int h_row_slot(const TLayout& L, int r) {
   return L.o_objpos + (r - L.nv);
 }
 
-template <int NVP>
-struct HTask : HEnv<NVP> {
-  using HEnv<NVP>::m; using HEnv<NVP>::sm; using HEnv<NVP>::e; using HEnv<NVP>::wid;
+template <int NVP, int BOX>
+struct HTask : HEnv<NVP, BOX> {
+  using HEnv<NVP, BOX>::m; using HEnv<NVP, BOX>::sm; using HEnv<NVP, BOX>::e; using HEnv<NVP, BOX>::wid;
 #define S(i) sm[(i) * HS + e]
   MMZ_DI int first_goal(int where) const {
     for (int g = 0; g < m->ngoal; g++) {
@@ -100,7 +100,7 @@ struct HTask : HEnv<NVP> {
 #undef S
 };
 
-template <int NVP, int MODE>
+template <int NVP, int BOX, int MODE>
 __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant__ TArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(h_smem_u32(smem)), "l"(A.model), "r"(L.model_bytes), "r"(h_smem_u32(&bar)) : "memory");
   }
-  HTask<NVP> T;
+  HTask<NVP, BOX> T;
   T.m = reinterpret_cast<const mmz_model*>(smem);
   T.dv = reinterpret_cast<const TDerived*>(smem + ((sizeof(mmz_model) + 15) & ~15));
   T.sm = ws;

@@ -18,8 +18,8 @@ flags = "-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcomp
 jobs = [(os.path.join(PKG, "csrc/mmz_api.cu"), "/tmp/dbg_api.o", [])]
 for g, n, f in INSTANCES:
     jobs.append((os.path.join(PKG, "csrc/mmz_inst.cu"), f"/tmp/dbg_{g}_{n}_{f}.o", [f"-DMMZ_G={g}", f"-DMMZ_NVP={n}", f"-DMMZ_FEAT={f}"]))
-for n in (14, 16):
-    jobs.append((os.path.join(PKG, "csrc/mmz_hinst.cu"), f"/tmp/dbg_h{n}.o", [f"-DMMZ_NVP={n}"]))
+for n, box in ((14, 0), (16, 1)):
+    jobs.append((os.path.join(PKG, "csrc/mmz_hinst.cu"), f"/tmp/dbg_h{n}.o", [f"-DMMZ_NVP={n}", f"-DMMZ_BOX={box}"]))
 
 
 def run(j):
