@@ -14,7 +14,7 @@ sys.path.insert(0, PKG)
 from build_native import INSTANCES  # noqa: E402
 
 extra = [a for a in sys.argv[1:] if a.startswith("-D")] or ["-DMMZ_DEBUG_UNIFORM"]
-flags = "-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC".split() + extra
+flags = "-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -prec-div=false -prec-sqrt=false -ftz=true -Xcompiler -fPIC".split() + extra
 jobs = [(os.path.join(PKG, "csrc/mmz_api.cu"), "/tmp/dbg_api.o", [])]
 for g, n, f in INSTANCES:
     jobs.append((os.path.join(PKG, "csrc/mmz_inst.cu"), f"/tmp/dbg_{g}_{n}_{f}.o", [f"-DMMZ_G={g}", f"-DMMZ_NVP={n}", f"-DMMZ_FEAT={f}"]))
