@@ -748,6 +748,9 @@ struct HEnv {
     float cd[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) cd[k] = me ? W_(L.o_cdof + 6 * lane + k) : 0.f;
+    float mrow[NVP];  // this lane's row of the mass matrix (zero outside the model)
+#pragma unroll
+    for (int k = 0; k < NVP; k++) mrow[k] = (me && k < nv) ? W_(L.o_M + lane * L.ldm + k) : 0.f;
     const float sm_ = me ? W_(L.o_smooth + lane) : 0.f;
     float al = (warmstart && me) ? W_(L.o_qacc + lane) : 0.f;
     if (!warmstart && me) W_(L.o_qacc + lane) = 0.f;
@@ -761,10 +764,8 @@ struct HEnv {
 #pragma unroll 1
     for (int it = 0; it < kTMaxNewton; it++) {
       float Ma = 0.f, mag = 0.f;
-      if (me) {
-#pragma unroll 2
-        for (int k = 0; k < nv; k++) { const float t = W_(L.o_M + lane * L.ldm + k) * W_(L.o_qacc + k); Ma += t; mag += fabsf(t); }
-      }
+#pragma unroll
+      for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_qacc + (k < nv ? k : 0)); Ma += t; mag += fabsf(t); }
       float grad = Ma - sm_, dadd = 0.f;
       mag += fabsf(sm_);
       float ljar[2];
@@ -785,7 +786,7 @@ struct HEnv {
       float hrow[NVP];
 #pragma unroll
       for (int k = 0; k < NVP; k++) {
-        const float mk = (me && k < nv) ? W_(L.o_M + lane * L.ldm + k) : 0.f;
+        const float mk = mrow[k];
         hrow[k] = (k == lane) ? (me ? mk + dadd : 1.f) : mk;
       }
 #pragma unroll 1
@@ -817,10 +818,8 @@ struct HEnv {
         contact_products(L, cd, dr, done ? 0 : ncon, ncw, 1, &dummy0, &dummy1);
         __syncwarp();
         float md = 0.f;
-        if (me) {
-#pragma unroll 2
-          for (int k = 0; k < nv; k++) md += W_(L.o_M + lane * L.ldm + k) * W_(L.o_dir + k);
-        }
+#pragma unroll
+        for (int k = 0; k < NVP; k++) md += mrow[k] * W_(L.o_dir + (k < nv ? k : 0));
         const float g0 = gsum16(me ? dr * (Ma - sm_) : 0.f), h0 = gsum16(me ? dr * md : 0.f);
         float lo = 0.f, hi = -1.f;
         bool lsdone = done || !constrained;
