@@ -753,7 +753,8 @@ struct HEnv {
     for (int k = 0; k < NVP; k++) mrow[k] = (me && k < nv) ? W_(L.o_M + lane * L.ldm + k) : 0.f;
     const float sm_ = me ? W_(L.o_smooth + lane) : 0.f;
     float al = (warmstart && me) ? W_(L.o_qacc + lane) : 0.f;
-    if (!warmstart && me) W_(L.o_qacc + lane) = 0.f;
+    if (!(fabsf(al) < kMaxVal)) al = 0.f;  // a blown-up environment restarts from zero
+    if (me) W_(L.o_qacc + lane) = al;
     const int nlim = __popc(gballot(limD[0] > 0.f)) + __popc(gballot(limD[1] > 0.f));
     if (lane == 0) {
       IW(L.o_cnt + TN_ITER) = 0; IW(L.o_cnt + TN_LIM) = nlim;
@@ -957,49 +958,54 @@ struct HEnv {
 #pragma unroll 1
     for (int i = 0; i < 4; i++) {
       forward(L, true);
-      // accumulate this stage, then move to the state of the next stage (or the final combination)
-      const float B = (i == 0 || i == 3) ? (1.f / 6.f) : (1.f / 3.f);
+      // accumulate this stage, then move to the state of the next stage (or the final combination). Two phases:
+      // the positions (on the configuration manifold, mj_integratePos) read the stage velocity, which the second
+      // phase overwrites; at the final combination they read the accumulated velocity, complete after the first.
+      // A non-finite acceleration counts as zero and marks the environment.
+      const float B = (i == 0 || i == 3) ? (1.f / 6.f) : (1.f / 3.f), A = (i == 0 || i == 1) ? 0.5f : 1.f;
       bool badacc = false;
 #pragma unroll 1
       for (int d = 0; d < nv; d++) badacc |= !(fabsf(S(L.o_qacc + d)) < kMaxVal);
       bad |= badacc;
-      __syncthreads();
-      for (int d = wid; d < nv; d += TW) {
-        float f = S(L.o_qacc + d);
-        if (badacc) { f = 0.f; S(L.o_qacc + d) = 0.f; }
-        S(L.o_accv + d) += B * S(L.o_qvel + d);
-        S(L.o_acca + d) += B * f;
-      }
-      __syncthreads();
-      const float A = (i == 0 || i == 1) ? 0.5f : 1.f;
       const int vsrc = (i == 3) ? L.o_accv : L.o_qvel, asrc = (i == 3) ? L.o_acca : L.o_qacc;
-      // positions first (they read the stage velocity), on the configuration manifold (mj_integratePos)
-      for (int j = wid; j < L.nj; j += TW) {
-        const int qa = m->jnt_qadr[j], d = m->jnt_dadr[j];
-        if (m->jnt_type[j] == MMZ_JNT_FREE) {
-#pragma unroll
-          for (int k = 0; k < 3; k++) S(L.o_qpos + qa + k) = S(L.o_q0 + qa + k) + h * A * S(vsrc + d + k);
-          float wv[3] = {A * S(vsrc + d + 3), A * S(vsrc + d + 4), A * S(vsrc + d + 5)};
-          float q[4] = {S(L.o_q0 + qa + 3), S(L.o_q0 + qa + 4), S(L.o_q0 + qa + 5), S(L.o_q0 + qa + 6)};
-          const float nw = norm3(wv), ang = h * nw;
-          quat_norm(q);
-          if (ang > 0.f) {
-            const float inv = 1.f / nw;
-            float ax[3] = {wv[0] * inv, wv[1] * inv, wv[2] * inv}, qr[4], q2[4];
-            axisangle2quat(qr, ax, ang);
-            quat_mul(q2, q, qr);
-#pragma unroll
-            for (int k = 0; k < 4; k++) q[k] = q2[k];
+#pragma unroll 1
+      for (int ph = 0; ph < 2; ph++) {
+        if (ph == 0) {
+          for (int d = wid; d < nv; d += TW) {
+            const float f = badacc ? 0.f : S(L.o_qacc + d);
+            S(L.o_accv + d) += B * S(L.o_qvel + d);
+            S(L.o_acca + d) += B * f;
           }
-#pragma unroll
-          for (int k = 0; k < 4; k++) S(L.o_qpos + qa + 3 + k) = q[k];
         } else {
-          S(L.o_qpos + qa) = S(L.o_q0 + qa) + h * A * S(vsrc + d);
+          for (int d = wid; d < nv; d += TW) S(L.o_qvel + d) = S(L.o_v0 + d) + h * A * (badacc && i != 3 ? 0.f : S(asrc + d));
         }
+        if ((i == 3) == (ph == 1)) {  // positions: first phase for the intermediate stages, second for the final one
+          for (int j = TW - 1 - wid; j < L.nj; j += TW) {
+            const int qa = m->jnt_qadr[j], d = m->jnt_dadr[j];
+            if (m->jnt_type[j] == MMZ_JNT_FREE) {
+#pragma unroll
+              for (int k = 0; k < 3; k++) S(L.o_qpos + qa + k) = S(L.o_q0 + qa + k) + h * A * S(vsrc + d + k);
+              float wv[3] = {A * S(vsrc + d + 3), A * S(vsrc + d + 4), A * S(vsrc + d + 5)};
+              float q[4] = {S(L.o_q0 + qa + 3), S(L.o_q0 + qa + 4), S(L.o_q0 + qa + 5), S(L.o_q0 + qa + 6)};
+              const float nw = norm3(wv), ang = h * nw;
+              quat_norm(q);
+              if (ang > 0.f) {
+                const float inv = 1.f / nw;
+                float ax[3] = {wv[0] * inv, wv[1] * inv, wv[2] * inv}, qr[4], q2[4];
+                axisangle2quat(qr, ax, ang);
+                quat_mul(q2, q, qr);
+#pragma unroll
+                for (int k = 0; k < 4; k++) q[k] = q2[k];
+              }
+#pragma unroll
+              for (int k = 0; k < 4; k++) S(L.o_qpos + qa + 3 + k) = q[k];
+            } else {
+              S(L.o_qpos + qa) = S(L.o_q0 + qa) + h * A * S(vsrc + d);
+            }
+          }
+        }
+        __syncthreads();
       }
-      __syncthreads();
-      for (int d = wid; d < nv; d += TW) S(L.o_qvel + d) = S(L.o_v0 + d) + h * A * S(asrc + d);
-      __syncthreads();
     }
     // derived arrays (xpos, contacts) deliberately stay at the 4th-stage state: SURVEY quirk Q15
     return bad || state_bad(L);
