@@ -1,7 +1,7 @@
 """mujoco_maze — B200-native batched maze-navigation environments.
 
 Same user-facing surface as kngwyu/mujoco-maze (reference mujoco_maze/__init__.py:
-importing the package registers `Point/Ant/Swimmer{Maze}-v{i}` with entry point
+importing the package registers `Point/Ant/Swimmer/Reacher{Maze}-v{i}` with entry point
 `mujoco_maze.maze_env:MazeEnv`), but `MazeEnv.step` advances N lock-step
 environments in one hand-written sm_100a CUDA kernel behind the C ABI of
 include/mmz.h. `gym` is used when installed; otherwise `mujoco_maze.gym` is a
@@ -19,6 +19,7 @@ except ImportError:
 from mujoco_maze.ant import AntEnv  # noqa: E402
 from mujoco_maze.maze_task import TaskRegistry  # noqa: E402
 from mujoco_maze.point import PointEnv  # noqa: E402
+from mujoco_maze.reacher import ReacherEnv  # noqa: E402
 from mujoco_maze.swimmer import SwimmerEnv  # noqa: E402
 
 __version__ = "0.2.0+b200.r1"
@@ -29,9 +30,8 @@ _AGENTS = (  # (id prefix, descriptor class, which Scaling field selects the maz
     ("Point", PointEnv, "point"),
     ("Ant", AntEnv, "ant"),
     ("Swimmer", SwimmerEnv, "swimmer"),
+    ("Reacher", ReacherEnv, "swimmer"),  # the reference keys Reacher on the swimmer scale too (__init__.py:51-64, quirk Q14)
 )
-# ReacherEnv (reference __init__.py:51-64, "not tested" per README.md:129-130) is out of
-# scope of the hot path this package rebuilds; its ids are intentionally not registered.
 
 
 def _register_all() -> None:

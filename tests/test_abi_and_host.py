@@ -120,8 +120,12 @@ def test_registered_ids_spaces_and_custom_task():
     assert np.allclose(env.action_space.high, 30.0)
     p = gym.make("PointUMaze-v1").unwrapped
     assert p.observation_space.shape == (7,) and np.allclose(p.action_space.high, [1.0, 0.25])
-    if ids is not None:
-        assert "Ant4Rooms-v0" in ids and "PointUMaze-v0" in ids
+    specs = gym.registry.env_specs if hasattr(gym, "registry") and hasattr(gym.registry, "env_specs") else None
+    if specs is not None:  # the in-repo shim: the reference registers 48 Point + 45 Ant + 26 Swimmer + 26 Reacher ids
+        assert len(specs) == 145
+        assert sum(k.startswith("Reacher") for k in specs) == 26 and sum(k.startswith("Ant") for k in specs) == 45
+    r = gym.make("ReacherUMaze-v0").unwrapped
+    assert r.observation_space.shape == (9,) and r.action_space.shape == (1,)  # reference tests/test_envs.py:63-64
 
     # README.md:79-127: a user-defined task registers and compiles (host-side reward falls back to Python)
     class GoalRewardEMaze(MazeTask):

@@ -24,7 +24,8 @@ pytestmark = pytest.mark.gpu
 ENV_IDS = ["PointUMaze-v0", "SwimmerUMaze-v0", "AntUMaze-v0", "Ant4Rooms-v0", "AntPush-v0", "Point4Rooms-v1", "PointPush-v0",
            # beyond the BASELINE configs: elevated mazes with platforms and a z-slide block, several
            # blocks (18 dofs: the one-warp-per-environment instance), sub-goal and object-distance rewards
-           "AntFall-v0", "PointFall-v0", "AntMultiPush-v0", "Ant2Rooms-v2", "PointBlockCarry-v0", "PointPushMaze-v1"]
+           "AntFall-v0", "PointFall-v0", "AntMultiPush-v0", "Ant2Rooms-v2", "PointBlockCarry-v0", "PointPushMaze-v1",
+           "ReacherUMaze-v0"]
 OUT = os.path.join(ROOT, "gpurun_out", "parity")
 
 
