@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libmmz.so")
-# (lanes per env, padded nv, FEAT bits: 1 box geoms, 2 fluid) - keep in step with MMZ_INSTANCES in csrc/mmz_api.cu
-INSTANCES = ((8, 4, 1), (8, 4, 3), (8, 8, 2), (8, 8, 3), (16, 14, 0), (16, 16, 0), (16, 16, 1), (16, 16, 3), (32, 20, 3))
+# (lanes per env, padded nv, FEAT bits: 1 box geoms, 2 fluid, 4 sphere pairs between moving bodies) - keep in step with MMZ_INSTANCES in csrc/mmz_api.cu
+INSTANCES = ((8, 4, 1), (8, 4, 7), (8, 8, 2), (8, 8, 7), (16, 14, 0), (16, 16, 1), (16, 16, 7), (32, 20, 7))
 # Division and square root use the approximate (2 ulp) instructions and denormals flush to zero: +3 % on the Ant step,
 # errors against the fp64 oracle unchanged (profiles/r1_parity.md). The transcendental functions (sincosf, powf, logf)
 # stay precise: -use_fast_math buys another 1.4 % but triples the median velocity error.

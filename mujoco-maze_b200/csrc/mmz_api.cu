@@ -40,7 +40,7 @@ typedef mmz::kernel_fn kernel_fn;
 }  // namespace
 
 // kernel instances (one translation unit each, see build_native.py INSTANCES)
-#define MMZ_INSTANCES(X) X(8, 4, 1) X(8, 4, 3) X(8, 8, 2) X(8, 8, 3) X(16, 14, 0) X(16, 16, 0) X(16, 16, 1) X(16, 16, 3) X(32, 20, 3)
+#define MMZ_INSTANCES(X) X(8, 4, 1) X(8, 4, 7) X(8, 8, 2) X(8, 8, 7) X(16, 14, 0) X(16, 16, 1) X(16, 16, 7) X(32, 20, 7)
 namespace mmz {
 hkernel_fn get_hkernel_14(int mode);
 hkernel_fn get_hkernel_16(int mode);
@@ -127,8 +127,29 @@ void make_layout(const mmz_model& m, int G, int NVP, int maxcon, Layout* out) {
   *out = L;
 }
 
+// sphere-sphere / sphere-capsule pairs between moving bodies that pass the contact filter, ordered like MuJoCo (lower
+// geom type first, then lower id). Returns -1 for a pair the kernels cannot handle (capsule-capsule), else the count.
+int list_pairs(const mmz_model& m, int* pa, int* pb, int cap) {
+  int n = 0;
+  if (!m.collision_on) return 0;  // option collision="predefined" without pairs (swimmer.xml, reacher.xml)
+  for (int g1 = 0; g1 < m.ngeom; g1++)
+    for (int g2 = g1 + 1; g2 < m.ngeom; g2++) {
+      const int b1 = m.geom_body[g1], b2 = m.geom_body[g2];
+      if (b1 == b2 || m.body_parent[b1] == b2 || m.body_parent[b2] == b1) continue;
+      if (!((m.geom_contype[g1] & m.geom_conaffinity[g2]) || (m.geom_contype[g2] & m.geom_conaffinity[g1]))) continue;
+      int a = g1, b = g2;
+      if (m.geom_type[a] > m.geom_type[b]) { a = g2; b = g1; }
+      if (m.geom_type[b] == MMZ_GEOM_BOX) continue;  // handled with the box geoms
+      if (m.geom_type[a] != MMZ_GEOM_SPHERE) return -1;
+      if (n < cap) { if (pa) pa[n] = a; if (pb) pb[n] = b; }
+      n++;
+    }
+  return n;
+}
+
 void make_derived(const mmz_model& m, Derived* d) {
   memset(d, 0, sizeof *d);
+  d->npair = std::min((int)MMZ_MAXPAIR, std::max(0, list_pairs(m, d->pair_a, d->pair_b, MMZ_MAXPAIR)));
   int nlev = 0;
   for (int b = 0; b < m.nbody; b++) {
     int mask = 0;
@@ -157,6 +178,11 @@ int validate(const mmz_model& m) {
     if (m.body_parent[b] >= b) return fail(MMZ_ERR_MODEL, "bodies must be ordered parents first");
   for (int j = 0; j < m.njnt; j++)
     if (m.jnt_type[j] == MMZ_JNT_BALL) return fail(MMZ_ERR_MODEL, "ball joints are not supported");
+  {
+    const int np = list_pairs(m, nullptr, nullptr, 0);
+    if (np < 0) return fail(MMZ_ERR_MODEL, "capsule-capsule contacts between moving bodies are not supported");
+    if (np > MMZ_MAXPAIR) return fail(MMZ_ERR_CAPACITY, "%d moving geom pairs exceed the capacity of %d", np, (int)MMZ_MAXPAIR);
+  }
   return MMZ_OK;
 }
 
@@ -307,6 +333,7 @@ int configure(mmz_env* h, int G, int NVP) {
   int nbox = 0;
   for (int g = 0; g < h->hm.ngeom; g++) nbox += h->hm.geom_type[g] == MMZ_GEOM_BOX;
   int maxcon = h->hm.collision_on ? (nbox ? std::min(40, 16 + 8 * nbox) : 16) : 1;  // 1 block: 24, 2: 32, 3+: 40
+  if (h->hm.collision_on && list_pairs(h->hm, nullptr, nullptr, 0) > 0) maxcon = std::min(40, maxcon + 8);  // object balls
   if (h->hm.ngeom <= 2 && nbox) maxcon = 16;
   make_layout(h->hm, G, NVP, maxcon, &h->L);
   int dev_smem = 0, sms = 0;
@@ -319,6 +346,7 @@ int configure(mmz_env* h, int G, int NVP) {
   int feat = 0;
   if (nbox) feat |= FEAT_BOX;
   if (h->hm.density > 0.f || h->hm.viscosity > 0.f) feat |= FEAT_FLUID;
+  if (list_pairs(h->hm, nullptr, nullptr, 0) > 0) feat |= FEAT_PAIR;
   if (!mmz::get_kernel(G, NVP, feat, 0)) feat = FEAT_ALL;
   h->feat = feat;
   for (int mode = 0; mode < 5; mode++) {

@@ -64,7 +64,8 @@ constexpr int kMaxNewton = 24;
 // the step is instruction-fetch sensitive, so a model only pays for what it uses)
 enum { FEAT_BOX = 1,    // box geoms on moving bodies (Point's arrow, movable blocks): box-box, plane-box
        FEAT_FLUID = 2,  // fluid drag (Swimmer: density / viscosity)
-       FEAT_ALL = 3 };
+       FEAT_PAIR = 4,   // sphere-sphere / sphere-capsule contacts between moving bodies (object balls)
+       FEAT_ALL = 7 };
 constexpr int kMaxLineSearch = 24;
 
 template <int G, int NVP, int FEAT>
@@ -637,6 +638,39 @@ struct Env {
         int base = ncon + incl - n;
         if (n > 0 && base < L.maxcon) write_contact(L, base, r0, b1, b2, iw, g, other);
         if (n > 1 && base + 1 < L.maxcon) write_contact(L, base + 1, r1, b1, b2, iw, g, other);
+        ncon += total;
+        if (ncon > L.maxcon) { ncon = L.maxcon; overflow = true; }
+      }
+    }
+    // ---- spheres against spheres / capsules on other moving bodies (object balls): one lane per listed pair
+    if constexpr ((FEAT & FEAT_PAIR) != 0) {
+#pragma unroll 1
+      for (int pbase = 0; pbase < dv->npair; pbase += G) {
+        const int p = pbase + lane;
+        RawContact rc;
+        int n = 0, ga = 0, gb = 0;
+        if (p < dv->npair) {
+          ga = dv->pair_a[p]; gb = dv->pair_b[p];
+          const float* c1 = w + L.o_gpos + 3 * ga;
+          float q[3];
+          if (m->geom_type[gb] == MMZ_GEOM_CAPSULE) {
+            const float* gp = w + L.o_gpos + 3 * gb;
+            const float* gm = w + L.o_gmat + 9 * gb;
+            const float hl = m->geom_size[gb][1];
+            const float p0[3] = {gp[0] + gm[2] * hl, gp[1] + gm[5] * hl, gp[2] + gm[8] * hl};
+            const float p1[3] = {gp[0] - gm[2] * hl, gp[1] - gm[5] * hl, gp[2] - gm[8] * hl};
+            segment_nearest(p0, p1, c1, q);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++) q[k] = w[L.o_gpos + 3 * gb + k];
+          }
+          n = sphere_sphere(c1, m->geom_size[ga][0], q, m->geom_size[gb][0], fmaxf(m->geom_margin[ga], m->geom_margin[gb]), &rc);
+        }
+        if (!__any_sync(kFull, n > 0)) continue;
+        int total, incl = gscan<G>(n, lane, &total);
+        const int base = ncon + incl - n;
+        if (n > 0 && base < L.maxcon)
+          write_contact(L, base, rc, m->geom_body[ga], m->geom_body[gb], m->geom_invweight[ga] + m->geom_invweight[gb], ga, gb);
         ncon += total;
         if (ncon > L.maxcon) { ncon = L.maxcon; overflow = true; }
       }

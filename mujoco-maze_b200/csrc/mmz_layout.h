@@ -44,12 +44,17 @@ enum {
 enum { N_CON = 0, N_LIM = 1, N_ITER = 2, N_OVERFLOW = 3,
        N_ITER_SUM = 4, N_LS_SUM = 5, N_CON_MAX = 6, N_CAPPED = 7, N_CNT = 8 };  // 4..7: accumulated over one env-step
 
+constexpr int MMZ_MAXPAIR = 32;
+
 struct Derived {            // appended to the model blob in device memory
   int32_t anc[MMZ_MAXBODY];  // bit a set in anc[b]: body a is b or an ancestor of b
   int32_t boxg[MMZ_MAXGEOM]; // geoms of type box on moving bodies
   int32_t nboxg;
   int32_t nlev;              // number of tree levels
-  int32_t pad[2];
+  int32_t npair;             // sphere-sphere / sphere-capsule pairs between moving bodies that pass the contact filter
+  int32_t pad[1];
+  int32_t pair_a[MMZ_MAXPAIR];  // the sphere (geom1 of the pair)
+  int32_t pair_b[MMZ_MAXPAIR];  // the other sphere or the capsule (geom2)
   float ident[9];            // identity rotation (static maze boxes)
   float padf[3];
 };

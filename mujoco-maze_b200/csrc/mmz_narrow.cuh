@@ -60,6 +60,28 @@ MMZ_DI int sphere_box(const float* c, float r, const float* bc, const float* bR,
   return 1;
 }
 
+// sphere against sphere: normal from sphere 1 to sphere 2, contact midway between the surfaces. The capsule case is
+// the sphere against the capsule-radius sphere at the segment point nearest to it (segment_nearest).
+MMZ_DI int sphere_sphere(const float* c1, float r1, const float* c2, float r2, float margin, RawContact* out) {
+  const float d[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
+  const float len = norm3(d), dist = len - r1 - r2;
+  if (dist > margin) return 0;
+  float nrm[3] = {0.f, 0.f, 1.f};
+  if (len > kMinVal) { const float inv = 1.f / len; nrm[0] = d[0] * inv; nrm[1] = d[1] * inv; nrm[2] = d[2] * inv; }
+  out->dist = dist;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { out->normal[k] = nrm[k]; out->pos[k] = c1[k] + nrm[k] * (r1 + 0.5f * dist); out->hint[k] = 0.f; }
+  return 1;
+}
+MMZ_DI void segment_nearest(const float* p0, const float* p1, const float* c, float* q) {
+  const float ab[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, ac[3] = {c[0] - p0[0], c[1] - p0[1], c[2] - p0[2]};
+  const float den = dot3(ab, ab);
+  float t = den > kMinVal ? dot3(ac, ab) / den : 0.f;
+  t = fminf(fmaxf(t, 0.f), 1.f);
+#pragma unroll
+  for (int k = 0; k < 3; k++) q[k] = p0[k] + t * ab[k];
+}
+
 MMZ_DI float box_excess_deriv(const float* a, const float* b, float t, const float* h) {
   float g = 0.f;
 #pragma unroll

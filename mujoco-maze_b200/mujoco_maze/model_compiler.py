@@ -638,6 +638,32 @@ def add_movable_block(sc: Scene, cell: MazeCell, i: int, j: int, s: float, x: fl
     return name
 
 
+def add_object_ball(sc: Scene, kind: Optional[str], i: int, j: int, x: float, y: float, size: float) -> str:
+    """Object ball body (reference maze_env.py:489-560): a sphere of radius `size` resting on the floor.
+
+    "hinge" (Point, point.py:32): slide x, slide y and an unlimited hinge about z, mass 1e-4 * size^3;
+    "freejoint" (Ant, ant.py:42): a free joint, mass from the default density. solimp 0.9 0.99 0.001 in both."""
+    name = f"objball_{i}_{j}"
+    body = Body(name=name, pos=np.array([x, y, 0.0]), quat=np.array([1.0, 0, 0, 0]), parent=-1)
+    attrs = dict(name=f"{name}_geom", type="sphere", size=f"{size}", pos=f"0.0 0.0 {size}", contype="1", conaffinity="1",
+                 solimp="0.9 0.99 0.001")
+    if kind == "hinge":
+        attrs["mass"] = f"{0.0001 * size ** 3}"
+        body.geoms.append(make_geom(attrs, sc.geom_default))
+        for jn, ax in (("x", "1 0 0"), ("y", "0 1 0")):
+            body.joints.append(make_joint(dict(name=f"{name}_{jn}", axis=ax, pos="0 0 0", type="slide"), sc.joint_default, False))
+        body.joints.append(make_joint(dict(name=f"{name}_rot", axis="0 0 1", pos="0 0 0", type="hinge", limited="false"),
+                                      sc.joint_default, False))
+    elif kind == "freejoint":
+        body.geoms.append(make_geom(attrs, sc.geom_default))
+        # <freejoint> takes no defaults (armature 0, damping 0) [EXT: MJCF reference]
+        body.joints.append(make_joint(dict(name=f"{name}_root", type="free"), {}, True))
+    else:
+        raise ValueError(f"OBJBALL_TYPE is not registered for {kind}")  # reference maze_env.py:188-191
+    sc.bodies.append(body)
+    return name
+
+
 def compile_maze_model(
     agent,  # AgentModel subclass (class attributes only are read)
     task,  # MazeTask instance
@@ -701,9 +727,7 @@ def compile_maze_model(
             elif cell.can_move():
                 obj_names.append(add_movable_block(sc, cell, i, j, s, x, y, h, height_offset))
             elif cell.is_object_ball():
-                raise NotImplementedError(
-                    "object balls (Billiard family) are scheduled after the BASELINE configs; "
-                    "see DESIGN.md 'out of scope this round'")
+                ball_names.append(add_object_ball(sc, agent.OBJBALL_TYPE, i, j, x, y, float(task.OBJECT_BALL_SIZE)))
 
     wall = make_geom(dict(type="box", contype="1", conaffinity="1"), sc.geom_default)
     floor = next((g for g in sc.world_geoms if g.type == L.GEOM_PLANE), None)
@@ -748,8 +772,9 @@ def compile_maze_model(
     gpos = np.zeros((len(goals), 3))
     for k, g in enumerate(goals):
         gpos[k, : g.dim] = np.asarray(g.pos, float)
-    observe = task.OBSERVE_BLOCKS
-    obs_bodies = [names["body"].index(n) for n in obj_names] if observe else []
+    # observed bodies, in the reference's order: balls, then blocks (maze_env.py:360-366)
+    obs_bodies = [names["body"].index(n) for n in ball_names] if task.OBSERVE_BALLS else []
+    obs_bodies += [names["body"].index(n) for n in obj_names] if task.OBSERVE_BLOCKS else []
     if len(obs_bodies) > L.CAPS["MAXOBJ"]:
         raise ValueError("too many observed bodies")
 

@@ -503,6 +503,26 @@ static int capsule_box(const double* p0, const double* p1, double r, const doubl
 
 /* box against box: separating-axis search, then face clipping or an edge-edge point.
  * Normal points from box A to box B. Up to 8 contacts. */
+/* sphere against sphere [EXT: mjc_SphereSphere]: normal from sphere 1 to sphere 2, contact midway between the surfaces */
+static int sphere_sphere(const double* c1, double r1, const double* c2, double r2, double margin, raw_contact* out) {
+  double d[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
+  double len = norm3(d), dist = len - r1 - r2;
+  if (dist > margin) return 0;
+  double n[3] = {0, 0, 1};
+  if (len > MINVAL) for (int k = 0; k < 3; k++) n[k] = d[k] / len;
+  out->dist = dist;
+  for (int k = 0; k < 3; k++) { out->normal[k] = n[k]; out->pos[k] = c1[k] + n[k] * (r1 + 0.5 * dist); out->hint[k] = 0; }
+  return 1;
+}
+/* sphere against capsule [EXT: mjc_SphereCapsule]: the sphere against the capsule-radius sphere at the segment point nearest to it */
+static int sphere_capsule(const double* c, double rs, const double* p0, const double* p1, double rc, double margin, raw_contact* out) {
+  double ab[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, ac[3] = {c[0] - p0[0], c[1] - p0[1], c[2] - p0[2]};
+  double den = dot3(ab, ab), t = den > MINVAL ? dot3(ac, ab) / den : 0.0;
+  t = t < 0 ? 0 : (t > 1 ? 1 : t);
+  double q[3] = {p0[0] + t * ab[0], p0[1] + t * ab[1], p0[2] + t * ab[2]};
+  return sphere_sphere(c, rs, q, rc, margin, out);
+}
+
 static int box_box(const double* ca, const double* Ra, const double* ha, const double* cb, const double* Rb,
                    const double* hb, double margin, raw_contact* out) {
   double A[3][3], B[3][3], d[3];
@@ -755,7 +775,7 @@ static void collision(ora_env* e) {
         if (code & MMZ_CELL_PLATFORM) { bc[2] = m->plat_z; collide_static_box(e, g, bc, m->wall_half, &wp); }
       }
   }
-  /* --- pairs of geoms on different moving bodies; supported when at least one is a box */
+  /* --- pairs of geoms on different moving bodies: anything against a box, sphere against sphere / capsule (object balls) */
   for (int g1 = 0; g1 < m->ngeom; g1++)
     for (int g2 = g1 + 1; g2 < m->ngeom; g2++) {
       int b1 = m->geom_body[g1], b2 = m->geom_body[g2];
@@ -763,7 +783,7 @@ static void collision(ora_env* e) {
       if (!((m->geom_contype[g1] & m->geom_conaffinity[g2]) || (m->geom_contype[g2] & m->geom_conaffinity[g1]))) continue;
       int a = g1, b = g2; /* order by type, like MuJoCo */
       if (m->geom_type[a] > m->geom_type[b]) { a = g2; b = g1; }
-      if (m->geom_type[b] != MMZ_GEOM_BOX) continue;
+      if (m->geom_type[b] != MMZ_GEOM_BOX && m->geom_type[a] != MMZ_GEOM_SPHERE) continue; /* capsule-capsule: not in any asset */
       geom_par pa, pb;
       contact_t proto;
       raw_contact rc[8];
@@ -771,7 +791,13 @@ static void collision(ora_env* e) {
       geom_params(m, b, &pb);
       mix_par(&pa, &pb, &proto);
       int n = 0;
-      if (m->geom_type[a] == MMZ_GEOM_SPHERE)
+      if (m->geom_type[a] == MMZ_GEOM_SPHERE && m->geom_type[b] == MMZ_GEOM_SPHERE)
+        n = sphere_sphere(e->gpos[a], m->geom_size[a][0], e->gpos[b], m->geom_size[b][0], proto.margin, rc);
+      else if (m->geom_type[a] == MMZ_GEOM_SPHERE && m->geom_type[b] == MMZ_GEOM_CAPSULE) {
+        double p0[3], p1[3];
+        capsule_ends(e, b, p0, p1);
+        n = sphere_capsule(e->gpos[a], m->geom_size[a][0], p0, p1, m->geom_size[b][0], proto.margin, rc);
+      } else if (m->geom_type[a] == MMZ_GEOM_SPHERE)
         n = sphere_box(e->gpos[a], m->geom_size[a][0], e->gpos[b], e->gmat[b], m->geom_size[b], proto.margin, rc);
       else if (m->geom_type[a] == MMZ_GEOM_CAPSULE) {
         double p0[3], p1[3];

@@ -25,7 +25,10 @@ ENV_IDS = ["PointUMaze-v0", "SwimmerUMaze-v0", "AntUMaze-v0", "Ant4Rooms-v0", "A
            # beyond the BASELINE configs: elevated mazes with platforms and a z-slide block, several
            # blocks (18 dofs: the one-warp-per-environment instance), sub-goal and object-distance rewards
            "AntFall-v0", "PointFall-v0", "AntMultiPush-v0", "Ant2Rooms-v2", "PointBlockCarry-v0", "PointPushMaze-v1",
-           "ReacherUMaze-v0"]
+           "ReacherUMaze-v0",
+           # object balls (Billiard family): hinge-type ball for Point, free-joint ball for Ant (20 dofs), sphere-sphere and
+           # sphere-capsule contacts between moving bodies, reward / termination on the ball position
+           "PointBilliard-v0", "PointSmallBilliard-v1", "AntSmallBilliard-v0"]
 OUT = os.path.join(ROOT, "gpurun_out", "parity")
 
 
@@ -57,7 +60,17 @@ def sample_states(model, env_id, n, rng):
         q[:, 3:7] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
         q[:, 7:15] += rng.uniform(-0.7, 0.7, size=(n, 8))
         v[:, :6] *= 2.0
-        if nq > 15:  # movable block: small offsets from its cell
+        if "Billiard" in env_id:  # free-joint ball: near its cell, on the floor; half of the ants right next to it
+            q0 = np.asarray(model.qpos0, float)[:nq]
+            q[:, 15:18] = q0[15:18] + np.stack([rng.uniform(-0.2, 0.2, n), rng.uniform(-0.2, 0.2, n), rng.uniform(-0.01, 0.05, n)], 1)
+            bq = np.concatenate([np.ones((n, 1)), rng.normal(scale=0.2, size=(n, 3))], axis=1)
+            q[:, 18:22] = bq / np.linalg.norm(bq, axis=1, keepdims=True)
+            v[:, 14:] = rng.normal(scale=0.3, size=(n, nv - 14))
+            ang = rng.uniform(0, 2 * np.pi, n // 2)
+            dist = rng.uniform(0.5, 1.0, n // 2)
+            q[: n // 2, 0] = q[: n // 2, 15] + dist * np.cos(ang)
+            q[: n // 2, 1] = q[: n // 2, 16] + dist * np.sin(ang)
+        elif nq > 15:  # movable block: small offsets from its cell
             q[:, 15:] = rng.uniform(-0.3, 0.3, size=(n, nq - 15))
             v[:, 14:] = rng.normal(scale=0.2, size=(n, nv - 14))
     elif env_id.startswith("Point"):
@@ -65,6 +78,13 @@ def sample_states(model, env_id, n, rng):
         q[:, 2] = rng.uniform(-np.pi, np.pi, size=n)
         if nq > 3:
             q[:, 3:] = rng.uniform(-0.2, 0.2, size=(n, nq - 3))
+        if "Billiard" in env_id:  # half of the agents right next to the ball (sphere-sphere and arrow-ball contacts)
+            bpos = np.asarray(model.body_pos, float)[int(np.asarray(model.obj_body)[0])]
+            r = 0.5 + float(np.asarray(model.geom_size)[int(model.ngeom) - 1][0])
+            ang = rng.uniform(0, 2 * np.pi, n // 2)
+            dist = rng.uniform(r - 0.15, r + 0.8, n // 2)
+            q[: n // 2, 0] = bpos[0] + q[: n // 2, 3] + dist * np.cos(ang)
+            q[: n // 2, 1] = bpos[1] + q[: n // 2, 4] + dist * np.sin(ang)
     else:  # swimmer
         q[:, 0:2] = rng.uniform(-1, 1, size=(n, 2))
         q[:, 2] = rng.uniform(-np.pi, np.pi, size=n)
