@@ -148,3 +148,31 @@ def test_registered_ids_spaces_and_custom_task():
                  kwargs=dict(model_cls=PointEnv, maze_task=GoalRewardEMaze, maze_size_scaling=4.0, inner_reward_scaling=0.0))
     e = gym.make("PointEMaze-vtest").unwrapped
     assert e.model.nseg > 0 and e.observation_space.shape == (7,)
+
+
+def test_every_registered_id_compiles_with_the_reference_shapes():
+    """reference tests/test_envs.py: every id makes; obs (30,) Ant / (7,) or (10,) Point / (11,) Swimmer / (9,) Reacher
+    unless the task observes blocks or balls; Point*-v2 sub-goal tasks have several goals."""
+    import mujoco_maze  # noqa: F401
+    from mujoco_maze import gym
+
+    specs = getattr(getattr(gym, "registry", None), "env_specs", None)
+    if specs is None:
+        pytest.skip("real gym installed: its registry also holds foreign ids")
+    base = {"Ant": 30, "Point": 7, "Swimmer": 11, "Reacher": 9}
+    n = 0
+    for env_id in sorted(specs):
+        env = gym.make(env_id).unwrapped
+        prefix = next(p for p in base if env_id.startswith(p))
+        extra = 3 * (len(env.movable_blocks) if env._observe_blocks else 0) + 3 * (len(env.object_balls) if env._observe_balls else 0)
+        want = base[prefix] + extra
+        if prefix in ("Swimmer", "Reacher"):  # their _get_obs takes ALL of qpos / qvel, block joints included (swimmer.py:49-53)
+            want = int(env.model.nq) + int(env.model.nv) + 1 + extra
+        assert env.observation_space.shape == (want,), env_id
+        assert env.has_extended_obs == (extra > 0 or env._top_down_view)
+        blob = env.model.blob(4)
+        assert len(blob) > 8000
+        n += 1
+    assert n == 145
+    for env_id in ("Point2Rooms-v2", "Point4Rooms-v2", "PointBilliard-v2"):  # reference tests/test_envs.py:39-50
+        assert len(gym.make(env_id).unwrapped._task.goals) > 1
