@@ -122,7 +122,7 @@ def test_registered_ids_spaces_and_custom_task():
     assert p.observation_space.shape == (7,) and np.allclose(p.action_space.high, [1.0, 0.25])
     specs = gym.registry.env_specs if hasattr(gym, "registry") and hasattr(gym.registry, "env_specs") else None
     if specs is not None:  # the in-repo shim: the reference registers 48 Point + 45 Ant + 26 Swimmer + 26 Reacher ids
-        assert len(specs) == 145
+        assert len([k for k in specs if not k.endswith("-vtest")]) == 145
         assert sum(k.startswith("Reacher") for k in specs) == 26 and sum(k.startswith("Ant") for k in specs) == 45
     r = gym.make("ReacherUMaze-v0").unwrapped
     assert r.observation_space.shape == (9,) and r.action_space.shape == (1,)  # reference tests/test_envs.py:63-64
@@ -161,7 +161,7 @@ def test_every_registered_id_compiles_with_the_reference_shapes():
         pytest.skip("real gym installed: its registry also holds foreign ids")
     base = {"Ant": 30, "Point": 7, "Swimmer": 11, "Reacher": 9}
     n = 0
-    for env_id in sorted(specs):
+    for env_id in sorted(k for k in specs if not k.endswith("-vtest")):  # (another test registers a custom id)
         env = gym.make(env_id).unwrapped
         prefix = next(p for p in base if env_id.startswith(p))
         extra = 3 * (len(env.movable_blocks) if env._observe_blocks else 0) + 3 * (len(env.object_balls) if env._observe_balls else 0)
