@@ -39,7 +39,7 @@ def _run(model, env_id, kernel, q, v, acts):
     return outs, qq.cpu().numpy(), vv.cpu().numpy(), cfg
 
 
-@pytest.mark.parametrize("env_id", ["AntUMaze-v0", "Ant4Rooms-v0"])
+@pytest.mark.parametrize("env_id", ["AntUMaze-v0", "Ant4Rooms-v0", "AntPush-v0", "AntFall-v0"])
 def test_hybrid_and_groups_kernels_agree(env_id):
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
@@ -61,3 +61,25 @@ def test_hybrid_and_groups_kernels_agree(env_id):
     np.testing.assert_allclose(oh[0][1], og[0][1], atol=1e-4)
     e3 = np.abs(qh - qg) / (1 + np.abs(qg))
     assert np.median(e3.max(1)) < 1e-4
+
+
+def test_kernel_selection_per_model():
+    """Which kernel serves which model (mmz_kernel_name): the hybrid for the Ant family with and without movable blocks,
+    the lanes-per-environment kernel (8 / 16 / 32 lanes) with only the features the model needs for everything else."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mujoco_maze.backend import BatchedSim
+
+    want = {
+        "AntUMaze-v0": "maze_hkernel<14,0>", "Ant4Rooms-v0": "maze_hkernel<14,0>", "AntPush-v0": "maze_hkernel<16,1>",
+        "AntFall-v0": "maze_hkernel<16,1>", "PointUMaze-v0": "maze_kernel<8,4,1>", "SwimmerUMaze-v0": "maze_kernel<8,8,2>",
+        "ReacherUMaze-v0": "maze_kernel<8,4,7>", "AntMultiPush-v0": "maze_kernel<32,20,7>", "PointBilliard-v0": "maze_kernel<8,8,7>",
+        "AntSmallBilliard-v0": "maze_kernel<32,20,7>",
+    }
+    got = {}
+    for env_id in want:
+        sim = BatchedSim(make_model(env_id), 32)
+        got[env_id] = sim.kernel_config["kernel"]
+        sim.close()
+    assert got == want
