@@ -226,7 +226,27 @@ class MazeEnv(gym.Env):
         info = {"position": i_np[:2].copy()}
         if has_inner:
             info["reward_forward"], info["reward_ctrl"] = float(i_np[2]), float(i_np[3])
-        return o, float(reward[0].item()), bool(int(done[0].item()) & 1), info
+        r = float(reward[0].item())
+        if not (self._host_reward or self._host_term):
+            # The scalar (reference-shaped) call returns Python floats like the reference: the outer reward is one of a
+            # few exact constants (PENALTY, 1.0, a goal's reward_scale; maze_task.py) that fp32 cannot represent, and the
+            # reference's tests compare it with `==` (tests/test_envs.py:32-36). Snap the kernel's value to the constant
+            # it is the fp32 image of; distances and the inner reward stay as computed on the device.
+            inner = 0.0
+            if has_inner:
+                inner = float(self._inner_reward_scaling) * (
+                    float(getattr(self.wrapped_env, "_forward_reward_weight", 1.0)) * float(i_np[2]) + float(i_np[3]))
+            outer = r - inner
+            for c in self._exact_outer_rewards():
+                if abs(outer - c) <= 2e-7 * max(1.0, abs(c)):  # within fp32 rounding of the constant
+                    r = inner + c
+                    break
+        return o, r, bool(int(done[0].item()) & 1), info
+
+    def _exact_outer_rewards(self):
+        consts = [float(self._task.PENALTY), 1.0, 0.0]
+        consts += [float(g.reward_scale) for g in self._task.goals]
+        return consts
 
     def _host_rules(self, obs, reward, done, info_t):
         """User-defined MazeTask.reward / termination (README custom-task recipe): evaluated on the host.
