@@ -84,6 +84,10 @@ struct TArgs {
 
 constexpr int HS = 33;  // row stride of the [slot][33] workspace
 
+// one out-of-line copy of the record writer (it has several call sites); `c` points at element (slot 0, env) of the
+// contact block, consecutive fields are HS floats apart
+static __device__ __noinline__ void write_contact_record(float* c, const RawContact& rc, int b1, int b2, float iw, const float* par);
+
 template <int NVP, int BOX>
 struct HEnv {
   const mmz_model* m;
@@ -371,25 +375,10 @@ struct HEnv {
   }
   // stores a narrow-phase record into contact slot `slot` (layout C_* of mmz_layout.h); the normal points
   // from body b1 (geom1) to body b2 (geom2), -1 = world
-  __device__ __noinline__ void write_contact(const TLayout& L, int slot, const RawContact& rc, int b1, int b2, float iw, int g, int other) {
-    const int o = L.o_con + slot * L.cstride;
-    float fr[9], par[9];
+  MMZ_DI void write_contact(const TLayout& L, int slot, const RawContact& rc, int b1, int b2, float iw, int g, int other) {
+    float par[9];
     mix_params(g, other, par);
-#pragma unroll
-    for (int k = 0; k < 3; k++) { fr[k] = rc.normal[k]; fr[3 + k] = rc.hint[k]; }
-    make_frame(fr);
-#pragma unroll
-    for (int k = 0; k < 3; k++) S(o + C_POS + k) = rc.pos[k];
-#pragma unroll
-    for (int k = 0; k < 9; k++) S(o + C_FRAME + k) = fr[k];
-    S(o + C_DIST) = rc.dist;
-    S(o + C_MARGIN) = par[0];
-    S(o + C_MU) = par[1];
-#pragma unroll
-    for (int k = 0; k < 7; k++) S(o + C_SOLREF + k) = par[2 + k];
-    S(o + C_INVW) = iw;
-    S(o + C_BODY1) = __int_as_float(b1);
-    S(o + C_BODY2) = __int_as_float(b2);
+    write_contact_record(sm + (L.o_con + slot * L.cstride) * HS + e, rc, b1, b2, iw, par);
   }
   // number of collision items: one per geom, then (BOX only) BCAND candidate slots per box geom
   static constexpr int BCELLS = 9;                       // maze cells a box geom can reach (3 x 3)
@@ -648,8 +637,8 @@ struct HEnv {
     limD[0] = limD[1] = 0.f; limA[0] = limA[1] = 0.f;
     const int jl = lane < L.nv ? m->dof_jnt[lane] : 0;
     const bool limited = lane < L.nv && m->jnt_limited[jl] && m->jnt_type[jl] >= MMZ_JNT_SLIDE;
-#pragma unroll 1
-    for (int s = 0; s < 2; s++) {
+#pragma unroll
+    for (int s = 0; s < 2; s++) {  // unrolled: limD / limA must stay in registers (no dynamic indexing)
       if (!limited) continue;
       const float q = W_(L.o_qpos + m->jnt_qadr[jl]);
       const float pos = s == 0 ? q - m->jnt_range[jl][0] : m->jnt_range[jl][1] - q, margin = m->jnt_margin[jl];
@@ -1013,5 +1002,24 @@ struct HEnv {
 #undef S
 #undef W_
 };
+
+static __device__ __noinline__ void write_contact_record(float* c, const RawContact& rc, int b1, int b2, float iw, const float* par) {
+  float fr[9];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { fr[k] = rc.normal[k]; fr[3 + k] = rc.hint[k]; }
+  make_frame(fr);
+#pragma unroll
+  for (int k = 0; k < 3; k++) c[(C_POS + k) * HS] = rc.pos[k];
+#pragma unroll
+  for (int k = 0; k < 9; k++) c[(C_FRAME + k) * HS] = fr[k];
+  c[C_DIST * HS] = rc.dist;
+  c[C_MARGIN * HS] = par[0];
+  c[C_MU * HS] = par[1];
+#pragma unroll
+  for (int k = 0; k < 7; k++) c[(C_SOLREF + k) * HS] = par[2 + k];
+  c[C_INVW * HS] = iw;
+  c[C_BODY1 * HS] = __int_as_float(b1);
+  c[C_BODY2 * HS] = __int_as_float(b2);
+}
 
 }  // namespace mmz
