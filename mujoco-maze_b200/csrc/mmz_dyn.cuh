@@ -690,7 +690,7 @@ struct Env {
   // box geoms after it - are split over the lanes of the group (box-box is long, serial code); a scan over
   // the lanes keeps the contact order (candidate-major) independent of the mapping. Warp-uniform call.
   // (Same run, 20 steps: PointUMaze 4096 envs 0.42 -> 0.35 ms, AntPush 32768 envs 29.4 -> 26.1 ms per step.)
-  __device__ __noinline__ void box_geom_contacts(const Layout& L, int g, int kbox) {
+  MMZ_DI void box_geom_contacts(const Layout& L, int g, int kbox) {
     int* cn = cnt(L);
     int ncon = cn[N_CON];
     bool overflow = false;
