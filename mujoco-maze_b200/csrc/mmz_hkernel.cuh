@@ -864,8 +864,56 @@ struct HEnv {
     __syncwarp();
   }
 
+  // RK4 bookkeeping of stage i for this warp's two environments (solver view, lane = dof), right after their solve:
+  // accumulate the stage (B weights), then move to the state of the next stage, or to the final combination after
+  // stage 3 (classic tableau, A = 1/2, 1/2, 1). Positions integrate on the configuration manifold (mj_integratePos):
+  // free-joint quaternion <- q (x) exp(h w / 2). A non-finite acceleration counts as zero and marks the environment.
+  MMZ_DI void rk_update_g(const TLayout& L, int i) {
+    const float hstep = m->timestep;
+    const float B = (i == 0 || i == 3) ? (1.f / 6.f) : (1.f / 3.f), A = (i == 0 || i == 1) ? 0.5f : 1.f;
+    const bool me = lane < L.nv;
+    float f = me ? W_(L.o_qacc + lane) : 0.f;
+    const bool badacc = gballot(me && !(fabsf(f) < kMaxVal)) != 0;
+    if (badacc) f = 0.f;
+    const float v = me ? W_(L.o_qvel + lane) : 0.f;
+    float av = 0.f, aa = 0.f;
+    if (me) {
+      av = W_(L.o_accv + lane) + B * v; aa = W_(L.o_acca + lane) + B * f;
+      W_(L.o_accv + lane) = av; W_(L.o_acca + lane) = aa;
+      W_(L.o_dir + lane) = (i == 3) ? av : v;  // the velocity that moves the positions (o_dir is free after the solve)
+      W_(L.o_qvel + lane) = W_(L.o_v0 + lane) + hstep * A * ((i == 3) ? aa : f);
+    }
+    if (badacc && lane == 0) IW(L.o_cnt + TN_BAD) = 1;
+    __syncwarp();
+#pragma unroll 1
+    for (int j = lane; j < L.nj; j += 16) {
+      const int qa = m->jnt_qadr[j], d = m->jnt_dadr[j];
+      if (m->jnt_type[j] == MMZ_JNT_FREE) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) W_(L.o_qpos + qa + k) = W_(L.o_q0 + qa + k) + hstep * A * W_(L.o_dir + d + k);
+        float wv[3] = {A * W_(L.o_dir + d + 3), A * W_(L.o_dir + d + 4), A * W_(L.o_dir + d + 5)};
+        float q[4] = {W_(L.o_q0 + qa + 3), W_(L.o_q0 + qa + 4), W_(L.o_q0 + qa + 5), W_(L.o_q0 + qa + 6)};
+        const float nw = norm3(wv), ang = hstep * nw;
+        quat_norm(q);
+        if (ang > 0.f) {
+          const float inv = 1.f / nw;
+          float ax[3] = {wv[0] * inv, wv[1] * inv, wv[2] * inv}, qr[4], q2[4];
+          axisangle2quat(qr, ax, ang);
+          quat_mul(q2, q, qr);
+#pragma unroll
+          for (int k = 0; k < 4; k++) q[k] = q2[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) W_(L.o_qpos + qa + 3 + k) = q[k];
+      } else {
+        W_(L.o_qpos + qa) = W_(L.o_q0 + qa) + hstep * A * W_(L.o_dir + d);
+      }
+    }
+    __syncwarp();
+  }
+
   // ------------------------------------------------------------------ mj_forward
-  MMZ_DI void forward(const TLayout& L, bool warmstart) {
+  MMZ_DI void forward(const TLayout& L, bool warmstart, int rk_stage = -1) {
     // A: tree levels (kinematics, motion axes, world inertia, RNE forward)
 #pragma unroll 1
     for (int lvl = 0; lvl < L.nlev; lvl++) {
@@ -913,6 +961,7 @@ struct HEnv {
     // solver view: warp w owns environments w and w + 16
     limit_rows_g(L);
     solve_g(L, warmstart);
+    if (rk_stage >= 0) rk_update_g(L, rk_stage);  // in the shadow of the wait for the slowest solve of the block
     __syncthreads();
   }
 
@@ -944,58 +993,10 @@ struct HEnv {
     for (int i = wid; i < nq; i += TW) S(L.o_q0 + i) = S(L.o_qpos + i);
     for (int d = wid; d < nv; d += TW) { S(L.o_v0 + d) = S(L.o_qvel + d); S(L.o_accv + d) = 0.f; S(L.o_acca + d) = 0.f; }
     __syncthreads();
+    if (wid == 0) I(L.o_cnt + TN_BAD) = 0;
 #pragma unroll 1
-    for (int i = 0; i < 4; i++) {
-      forward(L, true);
-      // accumulate this stage, then move to the state of the next stage (or the final combination). Two phases:
-      // the positions (on the configuration manifold, mj_integratePos) read the stage velocity, which the second
-      // phase overwrites; at the final combination they read the accumulated velocity, complete after the first.
-      // A non-finite acceleration counts as zero and marks the environment.
-      const float B = (i == 0 || i == 3) ? (1.f / 6.f) : (1.f / 3.f), A = (i == 0 || i == 1) ? 0.5f : 1.f;
-      bool badacc = false;
-#pragma unroll 1
-      for (int d = 0; d < nv; d++) badacc |= !(fabsf(S(L.o_qacc + d)) < kMaxVal);
-      bad |= badacc;
-      const int vsrc = (i == 3) ? L.o_accv : L.o_qvel, asrc = (i == 3) ? L.o_acca : L.o_qacc;
-#pragma unroll 1
-      for (int ph = 0; ph < 2; ph++) {
-        if (ph == 0) {
-          for (int d = wid; d < nv; d += TW) {
-            const float f = badacc ? 0.f : S(L.o_qacc + d);
-            S(L.o_accv + d) += B * S(L.o_qvel + d);
-            S(L.o_acca + d) += B * f;
-          }
-        } else {
-          for (int d = wid; d < nv; d += TW) S(L.o_qvel + d) = S(L.o_v0 + d) + h * A * (badacc && i != 3 ? 0.f : S(asrc + d));
-        }
-        if ((i == 3) == (ph == 1)) {  // positions: first phase for the intermediate stages, second for the final one
-          for (int j = TW - 1 - wid; j < L.nj; j += TW) {
-            const int qa = m->jnt_qadr[j], d = m->jnt_dadr[j];
-            if (m->jnt_type[j] == MMZ_JNT_FREE) {
-#pragma unroll
-              for (int k = 0; k < 3; k++) S(L.o_qpos + qa + k) = S(L.o_q0 + qa + k) + h * A * S(vsrc + d + k);
-              float wv[3] = {A * S(vsrc + d + 3), A * S(vsrc + d + 4), A * S(vsrc + d + 5)};
-              float q[4] = {S(L.o_q0 + qa + 3), S(L.o_q0 + qa + 4), S(L.o_q0 + qa + 5), S(L.o_q0 + qa + 6)};
-              const float nw = norm3(wv), ang = h * nw;
-              quat_norm(q);
-              if (ang > 0.f) {
-                const float inv = 1.f / nw;
-                float ax[3] = {wv[0] * inv, wv[1] * inv, wv[2] * inv}, qr[4], q2[4];
-                axisangle2quat(qr, ax, ang);
-                quat_mul(q2, q, qr);
-#pragma unroll
-                for (int k = 0; k < 4; k++) q[k] = q2[k];
-              }
-#pragma unroll
-              for (int k = 0; k < 4; k++) S(L.o_qpos + qa + 3 + k) = q[k];
-            } else {
-              S(L.o_qpos + qa) = S(L.o_q0 + qa) + h * A * S(vsrc + d);
-            }
-          }
-        }
-        __syncthreads();
-      }
-    }
+    for (int i = 0; i < 4; i++) forward(L, true, i);  // each evaluation ends with its RK4 stage update (rk_update_g)
+    bad |= I(L.o_cnt + TN_BAD) != 0;  // a non-finite acceleration in some stage
     // derived arrays (xpos, contacts) deliberately stay at the 4th-stage state: SURVEY quirk Q15
     return bad || state_bad(L);
   }
