@@ -17,7 +17,7 @@ typedef float mmz_real;
 #endif
 
 #define MMZ_MAGIC 0x4D4D5A31
-#define MMZ_VERSION 3
+#define MMZ_VERSION 4
 #define MMZ_MAXBODY 16
 #define MMZ_MAXJNT 20
 #define MMZ_MAXDOF 20
@@ -27,7 +27,7 @@ typedef float mmz_real;
 #define MMZ_MAXGOAL 4
 #define MMZ_MAXSEG 64
 #define MMZ_MAXCELL 144
-#define MMZ_MAXOBJ 4
+#define MMZ_MAXOBJ 8
 
 #define MMZ_JNT_FREE 0
 #define MMZ_JNT_BALL 1
@@ -44,6 +44,8 @@ typedef float mmz_real;
 #define MMZ_RESET_SWIMMER 2
 #define MMZ_CELL_WALL 1
 #define MMZ_CELL_PLATFORM 2
+#define MMZ_CELL_CHASM 4
+#define MMZ_VIEW_DIM 75
 /* resolved reward / termination rules */
 #define MMZ_REWARD_REACH 0         /* 1.0 if terminated else penalty        maze_task.py:110-111 */
 #define MMZ_REWARD_SCALED 1        /* first reached goal's reward_scale     maze_task.py:356-360 */
@@ -85,7 +87,9 @@ typedef struct mmz_model {
   int32_t n_agent_v; /* agent qvel entries copied to obs */
   int32_t nobj; /* observed bodies spliced after obs[:3] */
   int32_t reset_kind; /* MMZ_RESET_* */
-  int32_t obj_body[4];
+  int32_t nviewb; /* bodies latched for the top-down view after the observed ones: torso, then movable blocks */
+  int32_t view_dim; /* 0, or 75 = 5x5x3 top-down view between the state part of obs and t (maze_env.py:353-369) */
+  int32_t obj_body[8]; /* nobj observed bodies, then nviewb view bodies */
   int32_t body_parent[16]; /* -1 = world */
   int32_t body_jntadr[16];
   int32_t body_jntnum[16];
@@ -110,7 +114,7 @@ typedef struct mmz_model {
   int32_t act_dof[8];
   int32_t act_limited[8];
   int32_t goal_dim[4];
-  int32_t grid[144]; /* row-major, bit0 wall box, bit1 platform box */
+  int32_t grid[144]; /* row-major, bit0 wall box (BLOCK cell), bit1 platform box, bit2 CHASM cell */
   mmz_real timestep;
   mmz_real gravity[3];
   mmz_real density; /* fluid */
@@ -169,7 +173,7 @@ typedef struct mmz_model {
   mmz_real seg[64][4]; /* x1 y1 x2 y2 */
 } mmz_model;
 
-#define MMZ_MODEL_NINT 584
+#define MMZ_MODEL_NINT 590
 #define MMZ_MODEL_NREAL 1477
 
 #endif /* MMZ_MODEL_H */

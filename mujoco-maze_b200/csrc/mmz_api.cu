@@ -15,6 +15,7 @@
 #define MMZ_API_TU
 #include "mmz_kernels.cuh"
 #include "mmz_hstep.cuh"
+#include "mmz_view.cuh"
 
 using namespace mmz;
 
@@ -94,11 +95,11 @@ void make_layout(const mmz_model& m, int G, int NVP, int maxcon, Layout* out) {
   Layout L;
   memset(&L, 0, sizeof L);
   L.nb = m.nbody; L.nj = m.njnt; L.nv = m.nv; L.nq = m.nq; L.nu = m.nu; L.ng = m.ngeom; L.nobj = m.nobj;
-  L.obs_dim = m.obs_dim;
+  L.obs_dim = m.obs_dim; L.nlatch = m.nobj + m.nviewb; L.obs_core = m.obs_dim - m.view_dim;
   L.ldm = m.nv | 1;
   L.maxcon = maxcon;
   L.cstride = C_STRIDE;
-  L.nstate = m.nq + 2 * m.nv + 3 * m.nobj;
+  L.nstate = m.nq + 2 * m.nv + 3 * L.nlatch;
   int o = 0;
   auto take = [&](int n) { int r = o; o += n; return r; };
   L.o_qpos = take(L.nq); L.o_qvel = take(L.nv); L.o_ctrl = take(L.nu > 0 ? L.nu : 1);
@@ -117,8 +118,8 @@ void make_layout(const mmz_model& m, int G, int NVP, int maxcon, Layout* out) {
   L.o_smooth = take(L.nv); L.o_qacc = take(L.nv); L.o_dir = take(L.nv);
   L.o_con = take(L.maxcon * L.cstride);
   L.o_cnt = take(N_CNT);
-  L.o_objpos = take(3 * L.nobj > 0 ? 3 * L.nobj : 1);
-  L.o_obs = take(L.obs_dim);
+  L.o_objpos = take(3 * L.nlatch > 0 ? 3 * L.nlatch : 1);
+  L.o_obs = take(L.obs_core);
   // stride % 32 == G % 32 so that the groups of one warp fall on disjoint bank ranges
   int stride = round_up(o, 32) + (G % 32);
   if (stride - 32 >= o) stride -= 32;
@@ -169,10 +170,11 @@ int validate(const mmz_model& m) {
   if (m.real_bytes != 4) return fail(MMZ_ERR_MODEL, "blob must use the float layout (real_bytes=4), got %d", m.real_bytes);
   if (m.nbody < 1 || m.nbody > MMZ_MAXBODY || m.njnt < 1 || m.njnt > MMZ_MAXJNT || m.nv < 1 || m.nv > MMZ_MAXDOF ||
       m.nq < 1 || m.nq > MMZ_MAXQ || m.ngeom < 0 || m.ngeom > MMZ_MAXGEOM || m.nu < 0 || m.nu > MMZ_MAXACT ||
-      m.ngoal < 0 || m.ngoal > MMZ_MAXGOAL || m.nseg < 0 || m.nseg > MMZ_MAXSEG || m.nobj < 0 || m.nobj > MMZ_MAXOBJ ||
+      m.ngoal < 0 || m.ngoal > MMZ_MAXGOAL || m.nseg < 0 || m.nseg > MMZ_MAXSEG || m.nobj < 0 || m.nobj > 4 || m.nviewb < 0 || m.nobj + m.nviewb > MMZ_MAXOBJ ||
       m.grid_h * m.grid_w > MMZ_MAXCELL || m.grid_h < 1 || m.grid_w < 1)
     return fail(MMZ_ERR_CAPACITY, "model dimensions exceed the compiled capacities");
-  if (m.obs_dim != m.n_agent_q + m.n_agent_v + 3 * m.nobj + 1 || m.obs_dim > 64)
+  if ((m.view_dim != 0 && (m.view_dim != MMZ_VIEW_DIM || m.nviewb < 1)) ||
+      m.obs_dim != m.n_agent_q + m.n_agent_v + 3 * m.nobj + m.view_dim + 1 || m.obs_dim - m.view_dim > 64)
     return fail(MMZ_ERR_MODEL, "inconsistent obs_dim %d", m.obs_dim);
   for (int b = 0; b < m.nbody; b++)
     if (m.body_parent[b] >= b) return fail(MMZ_ERR_MODEL, "bodies must be ordered parents first");
@@ -183,6 +185,20 @@ int validate(const mmz_model& m) {
     if (np < 0) return fail(MMZ_ERR_MODEL, "capsule-capsule contacts between moving bodies are not supported");
     if (np > MMZ_MAXPAIR) return fail(MMZ_ERR_CAPACITY, "%d moving geom pairs exceed the capacity of %d", np, (int)MMZ_MAXPAIR);
   }
+  return MMZ_OK;
+}
+
+// MazeEnv.get_top_down_view for tasks with TOP_DOWN_VIEW (none in the reference's registry): a second small launch
+// fills the 75 view columns of the observations the step / reset / observe kernel has just written.
+int launch_view(mmz_env* h, int mode, const KArgs& A, cudaStream_t s) {
+  if (!h->hm.view_dim || !A.obs || (mode != MODE_STEP && mode != MODE_RESET && mode != MODE_OBSERVE)) return MMZ_OK;
+  ViewArgs V;
+  V.model = (const mmz_model*)h->d_model; V.state = h->d_state; V.mask = mode == MODE_RESET ? A.mask : nullptr;
+  V.obs = A.obs; V.n = h->n; V.npad = h->npad;
+  const int threads = 256, total = h->n * MMZ_VIEW_DIM;
+  maze_view_kernel<<<(total + threads - 1) / threads, threads, 0, s>>>(V);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
   return MMZ_OK;
 }
 
@@ -199,7 +215,7 @@ int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s) {
     h->tfn[mode]<<<h->npad / TE, TW * 32, h->smem_bytes, s>>>(T);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
-    return MMZ_OK;
+    return launch_view(h, mode, A, s);
   }
   A.L = h->L;
   A.model = h->d_model;
@@ -214,7 +230,7 @@ int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s) {
   h->fn[mode]<<<blocks, h->tpb, h->smem_bytes, s>>>(A);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
-  return MMZ_OK;
+  return launch_view(h, mode, A, s);
 }
 
 int nbox_geoms(const mmz_model& m) {
@@ -252,17 +268,18 @@ bool configure_h(mmz_env* h, int* rc) {
   TLayout L;
   memset(&L, 0, sizeof L);
   L.nb = m.nbody; L.nj = m.njnt; L.nv = m.nv; L.nq = m.nq; L.nu = m.nu; L.ng = m.ngeom; L.nobj = m.nobj; L.obs_dim = m.obs_dim;
+  L.nlatch = m.nobj + m.nviewb; L.obs_core = m.obs_dim - m.view_dim;
   int nlev = 0;
   for (int b = 0; b < m.nbody; b++)
     if (m.body_level[b] + 1 > nlev) nlev = m.body_level[b] + 1;
   L.nlev = nlev; L.ldm = m.nv + 1;
   L.cstride = C_STRIDE;
-  L.nstate = m.nq + 2 * m.nv + 3 * m.nobj;
+  L.nstate = m.nq + 2 * m.nv + 3 * L.nlatch;
   const int nitems = L.ng + nbox * (1 + 2 * 9 + (nbox - 1));  // HEnv::n_items
   int o = 0;
   auto take = [&](int n) { int r = o; o += n; return r; };
   L.o_cnt = take(TN_CNT);
-  L.o_qpos = take(L.nq); L.o_qvel = take(L.nv); L.o_qacc = take(L.nv); L.o_objpos = take(3 * L.nobj > 0 ? 3 * L.nobj : 1);
+  L.o_qpos = take(L.nq); L.o_qvel = take(L.nv); L.o_qacc = take(L.nv); L.o_objpos = take(3 * L.nlatch > 0 ? 3 * L.nlatch : 1);
   L.o_ctrl = take(L.nu > 0 ? L.nu : 1); L.o_act = take(L.nu > 0 ? L.nu : 1);
   L.o_q0 = take(L.nq); L.o_v0 = take(L.nv); L.o_accv = take(L.nv); L.o_acca = take(L.nv);
   L.o_xpos = take(3 * L.nb);
@@ -271,7 +288,7 @@ bool configure_h(mmz_env* h, int* rc) {
   L.o_vel = take(6 * L.nb);
   L.o_M = take(L.nv * L.ldm);
   L.o_smooth = take(L.nv); L.o_dir = take(L.nv);
-  L.o_gcnt = take(nitems); L.o_obs = take(L.obs_dim);
+  L.o_gcnt = take(nitems); L.o_obs = take(L.obs_core);
   // Last: the arrays that are dead once the mass matrix and the smooth forces exist (orientations, inertias, bias
   // accelerations and forces). The contact slots are written after that point and OVERLAY them, then run on.
   const int dead0 = o;

@@ -52,6 +52,7 @@ struct TDerived {               // appended to the model blob in device memory
 
 struct TLayout {
   int nb, nj, nv, nq, nu, ng, nobj, obs_dim, nlev;
+  int nlatch, obs_core;  // as in Layout (mmz_layout.h)
   int maxcon, cstride, ldm, nstate, nslots, model_bytes;
   int o_qpos, o_qvel, o_qacc, o_objpos;  // persisted rows, in this order
   int o_ctrl, o_q0, o_v0, o_accv, o_acca;

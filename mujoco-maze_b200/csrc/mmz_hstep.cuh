@@ -21,6 +21,10 @@ MMZ_DI int h_row_slot(const TLayout& L, int r) {
   return L.o_objpos + (r - L.nv);
 }
 
+// column of obs[N][obs_dim] for entry i of the assembled observation: the top-down view (written by the view kernel)
+// sits between the state part and the trailing t * 0.001 (maze_env.py:368-369)
+MMZ_DI int obs_column(const TLayout& L, int i) { return i == L.obs_core - 1 ? L.obs_dim - 1 : i; }
+
 template <int NVP, int BOX>
 struct HTask : HEnv<NVP, BOX> {
   using HEnv<NVP, BOX>::m; using HEnv<NVP, BOX>::sm; using HEnv<NVP, BOX>::e; using HEnv<NVP, BOX>::wid;
@@ -59,13 +63,13 @@ struct HTask : HEnv<NVP, BOX> {
   // observed bodies: the reference reads data.xpos, which is only as fresh as the last kinematics pass
   MMZ_DI void latch_objpos(const TLayout& L, bool on) {
     if (on)
-      for (int i = wid; i < 3 * L.nobj; i += TW) S(L.o_objpos + i) = S(L.o_xpos + 3 * m->obj_body[i / 3] + i % 3);
+      for (int i = wid; i < 3 * L.nlatch; i += TW) S(L.o_objpos + i) = S(L.o_xpos + 3 * m->obj_body[i / 3] + i % 3);
   }
   // MazeEnv._get_obs (maze_env.py:351-369) into the o_obs slots
   MMZ_DI void assemble_obs(const TLayout& L, int t, bool on) {
     const int naq = m->n_agent_q, nav = m->n_agent_v, no = 3 * L.nobj;
     if (on) {
-      for (int i = wid; i < L.obs_dim; i += TW) {
+      for (int i = wid; i < L.obs_core; i += TW) {
         float v;
         if (i < 3 && i < naq) v = S(L.o_qpos + i);
         else if (i < 3 + no) v = S(L.o_objpos + i - 3);
@@ -212,9 +216,9 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
     // ---- outputs: the block's observations are one contiguous chunk of obs[N][obs_dim]
     {
       const int nreal = min(TE, A.n - env0);
-      for (int idx = tid; idx < nreal * L.obs_dim; idx += TW * 32) {
-        const int ee = idx / L.obs_dim, i = idx - ee * L.obs_dim;
-        A.obs[(size_t)env0 * L.obs_dim + idx] = ws[(L.o_obs + i) * HS + ee];
+      for (int idx = tid; idx < nreal * L.obs_core; idx += TW * 32) {
+        const int ee = idx / L.obs_core, i = idx - ee * L.obs_core;
+        A.obs[(size_t)(env0 + ee) * L.obs_dim + obs_column(L, i)] = ws[(L.o_obs + i) * HS + ee];
       }
     }
     if (wid == 0) {
@@ -249,9 +253,9 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
     T.assemble_obs(L, t, true);
     __syncthreads();
     const int nreal = min(TE, A.n - env0);
-    for (int idx = tid; idx < nreal * L.obs_dim; idx += TW * 32) {
-      const int ee = idx / L.obs_dim, i = idx - ee * L.obs_dim;
-      A.obs[(size_t)env0 * L.obs_dim + idx] = ws[(L.o_obs + i) * HS + ee];
+    for (int idx = tid; idx < nreal * L.obs_core; idx += TW * 32) {
+      const int ee = idx / L.obs_core, i = idx - ee * L.obs_core;
+      A.obs[(size_t)(env0 + ee) * L.obs_dim + obs_column(L, i)] = ws[(L.o_obs + i) * HS + ee];
     }
   } else if (MODE == TMODE_RESET) {
     const bool on = A.mask == nullptr || (real && A.mask[env]);
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
     __syncthreads();
     if (on && wid == 0) { A.counters[env] = 0; A.counters[A.npad + env] = nreset; }
     if (A.obs && real && on)
-      for (int i = wid; i < L.obs_dim; i += TW) A.obs[(size_t)env * L.obs_dim + i] = S(L.o_obs + i);
+      for (int i = wid; i < L.obs_core; i += TW) A.obs[(size_t)env * L.obs_dim + obs_column(L, i)] = S(L.o_obs + i);
   } else if (MODE == TMODE_REFRESH) {  // after set_state: mj_forward refreshes the derived arrays
     for (int d = wid; d < L.nv; d += TW) S(L.o_qacc + d) = 0.f;
     __syncthreads();

@@ -121,14 +121,14 @@ struct Task : Env<G, NVP, FEAT> {
   // `on` selects the environments that latch (warp-uniform call, predicated stores).
   MMZ_DI void latch_objpos(const Layout& L, bool on) {
     if (on)
-      for (int i = lane; i < 3 * L.nobj; i += G) w[L.o_objpos + i] = w[L.o_xpos + 3 * m->obj_body[i / 3] + i % 3];
+      for (int i = lane; i < 3 * L.nlatch; i += G) w[L.o_objpos + i] = w[L.o_xpos + 3 * m->obj_body[i / 3] + i % 3];
     sync();
   }
   // MazeEnv._get_obs (maze_env.py:351-369) written straight to global memory, env-major
   MMZ_DI void write_obs(const Layout& L, float* obs_g, float* obs_s, int t, bool on) {
     const int naq = m->n_agent_q, nav = m->n_agent_v, no = 3 * L.nobj;
     if (on) {
-      for (int i = lane; i < L.obs_dim; i += G) {
+      for (int i = lane; i < L.obs_core; i += G) {
         float v;
         if (i < 3 && i < naq) v = w[L.o_qpos + i];
         else if (i < 3 + no) v = w[L.o_objpos + i - 3];
@@ -136,7 +136,7 @@ struct Task : Env<G, NVP, FEAT> {
         else if (i < naq + no + nav) v = w[L.o_qvel + i - naq - no];
         else v = t * 0.001f;
         obs_s[i] = v;
-        if (obs_g) obs_g[i] = v;
+        if (obs_g) obs_g[i == L.obs_core - 1 ? L.obs_dim - 1 : i] = v;  // the view kernel fills the gap before t
       }
     }
     sync();

@@ -61,6 +61,8 @@ struct Derived {            // appended to the model blob in device memory
 
 struct Layout {
   int nb, nj, nv, nq, nu, ng, nobj, obs_dim;
+  int nlatch;    // latched body positions: nobj observed + nviewb for the top-down view
+  int obs_core;  // obs_dim without the top-down view: what the step kernel assembles (the view kernel fills the rest)
   int ldm;      // row stride of M and H (odd)
   int maxcon;   // contact capacity per environment
   int cstride;  // floats per contact block (odd)

@@ -72,8 +72,6 @@ class MazeEnv(gym.Env):
         self._observe_balls = self._task.OBSERVE_BALLS
         self._top_down_view = self._task.TOP_DOWN_VIEW
         self._put_spin_near_agent = self._task.PUT_SPIN_NEAR_AGENT
-        if self._top_down_view:
-            raise NotImplementedError("TOP_DOWN_VIEW is False for every upstream task and is not rebuilt")
 
         self.wrapped_env = model_cls(file_path=None, **kwargs)
         self.model: MazeModel = compile_maze_model(
@@ -197,6 +195,18 @@ class MazeEnv(gym.Env):
     # ------------------------------------------------------------------ episode API
     def _get_obs(self):
         return self._out(self.sim.observe())
+
+    def get_top_down_view(self):
+        """The 5x5x3 egocentric raster (walls, chasms, movable blocks) of reference maze_env.py:262-349.
+
+        Computed on the GPU by `maze_view_kernel` for tasks with TOP_DOWN_VIEW and delivered as the 75 entries
+        before the trailing `t * 0.001` of the observation (maze_env.py:353-354, 369); this accessor reshapes them
+        to `[5, 5, 3]` (`[N, 5, 5, 3]` for a batch).
+        """
+        if not self._top_down_view:
+            raise ValueError("the task does not set TOP_DOWN_VIEW")
+        obs = self._get_obs()
+        return obs[..., -76:-1].reshape(*obs.shape[:-1], 5, 5, 3)
 
     def reset(self, seed: Optional[int] = None, return_info: bool = False, mask=None, **kwargs):
         if seed is not None:

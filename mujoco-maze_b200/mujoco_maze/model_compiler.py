@@ -722,6 +722,8 @@ def compile_maze_model(
             x, y = j * s - torso_x, i * s - torso_y
             if elevated and not cell.is_chasm():
                 grid[i * cols + j] |= L.CELL_PLATFORM
+            if cell.is_chasm():
+                grid[i * cols + j] |= L.CELL_CHASM
             if cell.is_block():
                 grid[i * cols + j] |= L.CELL_WALL
             elif cell.can_move():
@@ -775,8 +777,13 @@ def compile_maze_model(
     # observed bodies, in the reference's order: balls, then blocks (maze_env.py:360-366)
     obs_bodies = [names["body"].index(n) for n in ball_names] if task.OBSERVE_BALLS else []
     obs_bodies += [names["body"].index(n) for n in obj_names] if task.OBSERVE_BLOCKS else []
-    if len(obs_bodies) > L.CAPS["MAXOBJ"]:
+    if len(obs_bodies) > 4:
         raise ValueError("too many observed bodies")
+    # get_top_down_view (maze_env.py:262-349) reads the torso and every movable block from data.xpos
+    view_bodies = [names["body"].index("torso")] + [names["body"].index(n) for n in obj_names] if task.TOP_DOWN_VIEW else []
+    view_dim = L.VIEW_DIM if task.TOP_DOWN_VIEW else 0
+    if len(obs_bodies) + len(view_bodies) > L.CAPS["MAXOBJ"]:
+        raise ValueError("too many movable blocks for the top-down view")
 
     kind = agent.KERNEL_KIND
     if kind == "point":
@@ -787,7 +794,7 @@ def compile_maze_model(
         naq, nav, step_kind, reset_kind = flat["nq"], flat["nv"], L.STEP_TORQUE, L.RESET_SWIMMER
     else:
         raise ValueError(f"unknown agent kind {kind}")
-    obs_dim = naq + nav + 3 * len(obs_bodies) + 1
+    obs_dim = naq + nav + 3 * len(obs_bodies) + view_dim + 1
 
     segs = np.zeros((0, 4))
     if agent.MANUAL_COLLISION:
@@ -803,7 +810,7 @@ def compile_maze_model(
         collision_on=int(sc.collision_on), has_floor=int(floor is not None), elevated=int(elevated),
         reward_rule=reward_rule, term_rule=term_rule, max_episode_steps=max_episode_steps,
         obs_dim=obs_dim, n_agent_q=naq, n_agent_v=nav, nobj=len(obs_bodies), reset_kind=reset_kind,
-        obj_body=np.array(obs_bodies, dtype=np.int64), goal_dim=np.array([g.dim for g in goals], dtype=np.int64),
+        obj_body=np.array(obs_bodies + view_bodies, dtype=np.int64), nviewb=len(view_bodies), view_dim=view_dim, goal_dim=np.array([g.dim for g in goals], dtype=np.int64),
         grid=grid,
         timestep=sc.timestep, gravity=sc.gravity, density=sc.density, viscosity=sc.viscosity,
         inner_reward_scale=inner_reward_scaling, forward_reward_weight=forward_reward_weight,

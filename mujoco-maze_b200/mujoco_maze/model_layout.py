@@ -12,7 +12,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 
 MAGIC = 0x4D4D5A31  # 'MMZ1'
-VERSION = 3
+VERSION = 4
 
 CAPS = dict(
     MAXBODY=16,  # moving bodies (world excluded)
@@ -24,7 +24,7 @@ CAPS = dict(
     MAXGOAL=4,
     MAXSEG=64,  # wall segments of the manual clamp (registry max 48)
     MAXCELL=144,  # maze grid cells (registry max 9x9)
-    MAXOBJ=4,  # observed bodies spliced into obs (blocks / balls)
+    MAXOBJ=8,  # latched bodies: observed ones spliced into obs (blocks / balls, <= 4) + the top-down view's
 )
 
 # MuJoCo's enum values, kept so that model dumps read familiar.
@@ -33,7 +33,8 @@ GEOM_PLANE, GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX = 0, 2, 3, 6
 
 STEP_TORQUE, STEP_TELEPORT = 0, 1  # AntEnv/SwimmerEnv.step vs PointEnv.step
 RESET_POINT, RESET_ANT, RESET_SWIMMER = 0, 1, 2
-CELL_WALL, CELL_PLATFORM = 1, 2  # bit flags of grid[]
+CELL_WALL, CELL_PLATFORM, CELL_CHASM = 1, 2, 4  # bit flags of grid[]
+VIEW_DIM = 75  # 5 x 5 x 3 egocentric raster (maze_env.py:95)
 
 B, J, D, Q, G, A, GO, S, C, O = (
     CAPS["MAXBODY"], CAPS["MAXJNT"], CAPS["MAXDOF"], CAPS["MAXQ"], CAPS["MAXGEOM"],
@@ -70,7 +71,9 @@ INT_FIELDS: List[Tuple[str, Tuple[int, ...], str]] = [
     ("n_agent_v", (), "agent qvel entries copied to obs"),
     ("nobj", (), "observed bodies spliced after obs[:3]"),
     ("reset_kind", (), "MMZ_RESET_*"),
-    ("obj_body", (O,), ""),
+    ("nviewb", (), "bodies latched for the top-down view after the observed ones: torso, then movable blocks"),
+    ("view_dim", (), "0, or 75 = 5x5x3 top-down view between the state part of obs and t (maze_env.py:353-369)"),
+    ("obj_body", (O,), "nobj observed bodies, then nviewb view bodies"),
     ("body_parent", (B,), "-1 = world"),
     ("body_jntadr", (B,), ""),
     ("body_jntnum", (B,), ""),
@@ -95,7 +98,7 @@ INT_FIELDS: List[Tuple[str, Tuple[int, ...], str]] = [
     ("act_dof", (A,), ""),
     ("act_limited", (A,), ""),
     ("goal_dim", (GO,), ""),
-    ("grid", (C,), "row-major, bit0 wall box, bit1 platform box"),
+    ("grid", (C,), "row-major, bit0 wall box (BLOCK cell), bit1 platform box, bit2 CHASM cell"),
 ]
 
 REAL_FIELDS: List[Tuple[str, Tuple[int, ...], str]] = [
@@ -257,6 +260,8 @@ def header_text() -> str:
         f"#define MMZ_RESET_SWIMMER {RESET_SWIMMER}",
         f"#define MMZ_CELL_WALL {CELL_WALL}",
         f"#define MMZ_CELL_PLATFORM {CELL_PLATFORM}",
+        f"#define MMZ_CELL_CHASM {CELL_CHASM}",
+        f"#define MMZ_VIEW_DIM {VIEW_DIM}",
         "/* resolved reward / termination rules (SURVEY.md section 8(a) row A9) */",
         "#define MMZ_REWARD_REACH 0         /* 1.0 if terminated else penalty        maze_task.py:110-111 */",
         "#define MMZ_REWARD_SCALED 1        /* first reached goal's reward_scale     maze_task.py:356-360 */",

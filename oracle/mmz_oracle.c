@@ -1101,6 +1101,38 @@ static int seg_detect(const mmz_model* m, const double* o, const double* n, doub
 }
 
 /* ------------------------------------------------------------------ obs / reward / termination */
+/* update_view of get_top_down_view (maze_env.py:268-322): a unit square around the source's continuous
+ * (row, col) is distributed over the 3x3 neighbourhood of its integer cell; out-of-raster parts are dropped. */
+static void view_splat(double view[5][5][3], double x, double y, int d, double robot_x, double robot_y, double s) {
+  x -= robot_x; y -= robot_y;                                      /* :270-271 */
+  const double rowc = 2 + (y + s / 2) / s, colc = 2 + (x + s / 2) / s; /* _xy_to_rowcol, :90-93 */
+  const int row = (int)rowc, col = (int)colc;                      /* int(): toward zero, :277 */
+  const double rf = rowc - floor(rowc), cf = colc - floor(colc);   /* Python `% 1` is never negative */
+  const double wr[3] = {fmax(0.0, 0.5 - rf), fmin(1.0, rf + 0.5) - fmax(0.0, rf - 0.5), fmax(0.0, rf - 0.5)};
+  const double wc[3] = {fmax(0.0, 0.5 - cf), fmin(1.0, cf + 0.5) - fmax(0.0, cf - 0.5), fmax(0.0, cf - 0.5)};
+  for (int a = -1; a <= 1; a++)
+    for (int b = -1; b <= 1; b++) {
+      const int r = row + a, c = col + b;
+      if (r >= 0 && r < 5 && c >= 0 && c < 5) view[r][c][d] += wr[a + 1] * wc[b + 1]; /* the nine cases :284-322 */
+    }
+}
+/* get_top_down_view (maze_env.py:262-349): channel 0 BLOCK cells, 1 CHASM cells, 2 movable blocks, all relative
+ * to the torso's data.xpos (view body 0); movable blocks are view bodies 1.. */
+static void top_down_view(const ora_env* e, double* out) {
+  const mmz_model* m = &e->m;
+  double view[5][5][3];
+  memset(view, 0, sizeof view);
+  const int* vb = m->obj_body + m->nobj;
+  const double rx = e->xpos[vb[0]][0], ry = e->xpos[vb[0]][1], s = m->cell_size;
+  for (int i = 0; i < m->grid_h; i++)
+    for (int j = 0; j < m->grid_w; j++) {
+      const int cell = m->grid[i * m->grid_w + j];
+      if (cell & MMZ_CELL_WALL) view_splat(view, j * s - m->origin[0], i * s - m->origin[1], 0, rx, ry, s);
+      if (cell & MMZ_CELL_CHASM) view_splat(view, j * s - m->origin[0], i * s - m->origin[1], 1, rx, ry, s);
+    }
+  for (int k = 1; k < m->nviewb; k++) view_splat(view, e->xpos[vb[k]][0], e->xpos[vb[k]][1], 2, rx, ry, s);
+  memcpy(out, view, sizeof view);
+}
 static void observe(const ora_env* e, double* obs) {
   const mmz_model* m = &e->m;
   int k = 0;
@@ -1108,6 +1140,7 @@ static void observe(const ora_env* e, double* obs) {
   for (int o = 0; o < m->nobj; o++) for (int i = 0; i < 3; i++) obs[k++] = e->xpos[m->obj_body[o]][i];
   for (int i = 3; i < m->n_agent_q; i++) obs[k++] = e->qpos[i];
   for (int i = 0; i < m->n_agent_v; i++) obs[k++] = e->qvel[i];
+  if (m->view_dim) { top_down_view(e, obs + k); k += MMZ_VIEW_DIM; } /* maze_env.py:353-354,369 */
   obs[k++] = e->t * 0.001;
 }
 static int first_goal(const mmz_model* m, const double* where) {
@@ -1283,7 +1316,7 @@ long ora_rollout(const void* blob, size_t bytes, int n, const double* qpos, cons
 #endif
   for (int i = 0; i < n; i++) {
     ora_env* e = ora_create(blob, bytes);
-    double obs[64], r = 0, info[4];
+    double obs[64 + MMZ_VIEW_DIM], r = 0, info[4];
     ora_set_state(e, qpos + (size_t)i * nq, qvel + (size_t)i * nv, 0);
     for (int s = 0; s < steps; s++) {
       ora_step(e, actions + ((size_t)s * n + i) * nu, obs, &r, info);
