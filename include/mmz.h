@@ -122,6 +122,12 @@ int mmz_forward(mmz_handle h, const float* d_action, float* d_qacc, int32_t* d_d
  * that hit the iteration cap}, summed over the forward evaluations of that step. NULL disables. */
 int mmz_set_step_diag(mmz_handle h, int32_t* d_diag);
 
+/* MazeEnv.render(mode="rgb_array") (maze_env.py:389-420) for environments [first_env, first_env + count): an
+ * orthographic top-down RGB image of each (floor / platforms / chasms, maze boxes, goal sites, agent geoms, movable
+ * blocks, object balls), d_rgb [count][height][width][3] uint8, row 0 = largest y. The window is the maze's bounding
+ * box plus half a cell. One launch; the reference reads one OpenGL frame per call. No pixel parity is claimed. */
+int mmz_render(mmz_handle h, int first_env, int count, int width, int height, uint8_t* d_rgb, void* stream);
+
 /* Number of CUDA kernels this handle has launched so far. */
 uint64_t mmz_launch_count(mmz_handle h);
 

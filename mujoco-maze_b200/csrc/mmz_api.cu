@@ -16,6 +16,7 @@
 #include "mmz_kernels.cuh"
 #include "mmz_hstep.cuh"
 #include "mmz_view.cuh"
+#include "mmz_render.cuh"
 
 using namespace mmz;
 
@@ -403,7 +404,7 @@ int configure(mmz_env* h, int G, int NVP) {
 
 extern "C" {
 
-int mmz_abi_version(void) { return 4; }
+int mmz_abi_version(void) { return 5; }
 const char* mmz_last_error(void) { return g_err; }
 
 int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, uint32_t flags, mmz_handle* out) {
@@ -587,6 +588,23 @@ int mmz_observe(mmz_handle h, float* d_obs, void* stream) {
   memset(&A, 0, sizeof A);
   A.obs = d_obs;
   return launch(h, MODE_OBSERVE, A, (cudaStream_t)stream);
+}
+
+int mmz_render(mmz_handle h, int first_env, int count, int width, int height, uint8_t* d_rgb, void* stream) {
+  if (!h || !d_rgb) return fail(MMZ_ERR_INVALID, "null argument");
+  if (first_env < 0 || count < 1 || first_env + count > h->n) return fail(MMZ_ERR_INVALID, "environment range out of bounds");
+  if (width < 1 || height < 1 || width > 4096 || height > 4096) return fail(MMZ_ERR_INVALID, "image size must be 1..4096");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const mmz_model& m = h->hm;
+  RenderArgs R;
+  R.model = (const mmz_model*)h->d_model; R.state = h->d_state; R.rgb = d_rgb;
+  R.npad = h->npad; R.first_env = first_env; R.count = count; R.width = width; R.height = height;
+  R.x0 = -m.origin[0] - m.cell_size; R.x1 = (m.grid_w - 1) * m.cell_size - m.origin[0] + m.cell_size;
+  R.y0 = -m.origin[1] - m.cell_size; R.y1 = (m.grid_h - 1) * m.cell_size - m.origin[1] + m.cell_size;
+  maze_render_kernel<<<count, 256, 0, (cudaStream_t)stream>>>(R);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MMZ_OK;
 }
 
 int mmz_get_state(mmz_handle h, int layout, float* d_qpos, float* d_qvel, int32_t* d_t, void* stream) {

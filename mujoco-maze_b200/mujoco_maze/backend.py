@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_PKG_ROOT, os.environ.get("MMZ_LIB", "libmmz.so"))
 MMZ_DONE, MMZ_TRUNCATED, MMZ_UNSTABLE = 1, 2, 4
 MMZ_AUTO_RESET = 1
 LAYOUT_ENV_MAJOR, LAYOUT_SOA = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _lib = None
 
@@ -57,6 +57,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "mmz_get_state": ([vp, i32, vp, vp, vp, vp], i32),
         "mmz_set_state": ([vp, i32, vp, vp, vp, vp], i32),
         "mmz_forward": ([vp, vp, vp, vp, vp], i32),
+        "mmz_render": ([vp, i32, i32, i32, i32, vp, vp], i32),
         "mmz_launch_count": ([vp], u64),
         "mmz_last_error": ([], ctypes.c_char_p),
         "mmz_destroy": ([vp], None),
@@ -74,7 +75,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = (
     "mmz_create", "mmz_dims", "mmz_kernel_config", "mmz_kernel_name", "mmz_set_env_offset", "mmz_set_step_diag", "mmz_reset", "mmz_step", "mmz_step_host", "mmz_observe", "mmz_get_state",
-    "mmz_set_state", "mmz_forward", "mmz_launch_count", "mmz_last_error", "mmz_destroy", "mmz_abi_version",
+    "mmz_set_state", "mmz_forward", "mmz_render", "mmz_launch_count", "mmz_last_error", "mmz_destroy", "mmz_abi_version",
 )
 
 
@@ -187,6 +188,15 @@ class BatchedSim:
         diag = t.empty((self.n, 4), dtype=t.int32, device=self.device)
         self._check(self.lib.mmz_forward(self._h, a.data_ptr(), qacc.data_ptr(), diag.data_ptr(), self._stream()))
         return qacc, diag
+
+    def render(self, width: int = 256, height: int = 256, first_env: int = 0, count: Optional[int] = None):
+        """Top-down RGB images of environments [first_env, first_env + count): uint8 [count, height, width, 3]."""
+        t = self.torch
+        count = self.n - first_env if count is None else int(count)
+        rgb = t.empty((count, height, width, 3), dtype=t.uint8, device=self.device)
+        self._check(self.lib.mmz_render(self._h, int(first_env), count, int(width), int(height), rgb.data_ptr(),
+                                        self._stream()))
+        return rgb
 
     def enable_step_diag(self, on: bool = True):
         """Per-env solver diagnostics of every following step: [N, 4] int32 (see include/mmz.h)."""

@@ -129,6 +129,9 @@ class Wrapper(Env):
     def reset(self, **kwargs):
         return self.env.reset(**kwargs)
 
+    def render(self, mode="human", **kwargs):
+        return self.env.render(mode=mode, **kwargs)
+
     def close(self):
         return self.env.close()
 

@@ -277,8 +277,24 @@ class MazeEnv(gym.Env):
         return (torch.as_tensor(r, dtype=torch.float32, device=reward.device),
                 torch.as_tensor(d, dtype=torch.uint8, device=done.device))
 
-    def render(self, mode="human", **kwargs) -> Any:
-        raise NotImplementedError("rendering / the websocket viewer are outside the rebuilt hot path (DESIGN.md)")
+    def render(self, mode="rgb_array", width: int = 256, height: int = 256, env_ids: Any = None, **kwargs) -> Any:
+        """Top-down RGB image(s) from the batched CUDA rasteriser (`mmz_render`).
+
+        The reference renders through MuJoCo's OpenGL context (maze_env.py:389-420); here every requested
+        environment is drawn by one kernel launch. `mode="rgb_array"`: uint8 `[height, width, 3]` numpy array for a
+        single environment, `[count, height, width, 3]` CUDA tensor for a batch (`env_ids`: None = all, an int, or a
+        `(first, count)` range). `mode="human"` (an on-screen / websocket viewer) is not rebuilt.
+        """
+        if mode != "rgb_array":
+            raise NotImplementedError("only mode='rgb_array' is rebuilt; the on-screen and websocket viewers are not")
+        if env_ids is None:
+            first, count = 0, self.num_envs
+        elif isinstance(env_ids, int):
+            first, count = env_ids, 1
+        else:
+            first, count = env_ids
+        rgb = self.sim.render(width, height, first, count)
+        return rgb if self.is_batched else rgb[0].cpu().numpy()
 
     def close(self) -> None:
         if self._sim is not None:
