@@ -338,6 +338,20 @@ void make_tderived(const mmz_model& m, TDerived* d) {
       if (m.body_level[b] == l) d->lvl_body[k++] = b;
   }
   d->lvl_off[nlev] = k;
+  {
+    int owner[MMZ_MAXBODY], nl1 = 0, n = 0;
+    for (int b = 0; b < m.nbody; b++) {  // parents come first in the blob
+      owner[b] = -1;
+      if (m.body_level[b] == 1) owner[b] = nl1++ % TW;
+      else if (m.body_level[b] > 1) owner[b] = owner[m.body_parent[b]];
+    }
+    for (int w = 0; w < TW; w++) {
+      d->chain_off[w] = n;
+      for (int b = 0; b < m.nbody; b++)
+        if (owner[b] == w) d->chain_body[n++] = b;
+    }
+    d->chain_off[TW] = n;
+  }
   d->ident[0] = d->ident[4] = d->ident[8] = 1.f;
   for (int g = 0; g < MMZ_MAXGEOM; g++) d->boxord[g] = -1;
   for (int g = 0; g < m.ngeom; g++)

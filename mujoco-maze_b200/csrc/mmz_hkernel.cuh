@@ -46,6 +46,11 @@ struct TDerived {               // appended to the model blob in device memory
   int32_t nboxg;
   int32_t nlev;
   int32_t pad[2];
+  // bodies below the roots, grouped by the warp that walks them: the subtree of the k-th level-1 body belongs to
+  // warp k % TW, parents first, so a chain needs no block barrier (lane e of one warp reads what it wrote)
+  int32_t chain_off[TW + 1];
+  int32_t chain_body[MMZ_MAXBODY];
+  int32_t pad2[3];
   float ident[9];
   float padf[3];
 };
@@ -804,6 +809,7 @@ struct HEnv {
       __syncwarp();
       float alpha = 1.f;
       int ls = 0;
+      bool exact = false;
       if (__any_sync(kAll, constrained && !done)) {
         float dummy0 = 0.f, dummy1 = 0.f;
         contact_products(L, cd, dr, done ? 0 : ncon, ncw, 1, &dummy0, &dummy1);
@@ -814,26 +820,31 @@ struct HEnv {
         const float g0 = gsum16(me ? dr * (Ma - sm_) : 0.f), h0 = gsum16(me ? dr * md : 0.f);
         float lo = 0.f, hi = -1.f;
         bool lsdone = done || !constrained;
+        bool flipped = true, lsconv = false;  // did a row change sides between 0 and alpha; did the search converge
 #pragma unroll 1
         for (int k = 0; k < kTMaxLineSearch; k++) {
           float g = 0.f, h = 0.f;
+          bool fl = false;
 #pragma unroll
           for (int s = 0; s < 2; s++) {
             const float jv = s == 0 ? dr : -dr, x = ljar[s] + alpha * jv;
             if (limD[s] > 0.f && x < 0.f) { g += limD[s] * x * jv; h += limD[s] * jv * jv; }
+            fl |= limD[s] > 0.f && (x < 0.f) != (ljar[s] < 0.f);
           }
           if (!lsdone) {
 #pragma unroll 1
             for (int r = lane; r < 4 * ncon; r += 16) {
               const int cs = L.o_con + (r >> 2) * L.cstride;
-              const float jv = W_(cs + C_JV + (r & 3)), x = W_(cs + C_JAR + (r & 3)) + alpha * jv, D = W_(cs + C_D);
+              const float jv = W_(cs + C_JV + (r & 3)), jar = W_(cs + C_JAR + (r & 3)), x = jar + alpha * jv, D = W_(cs + C_D);
               if (x < 0.f) { g += D * x * jv; h += D * jv * jv; }
+              fl |= (x < 0.f) != (jar < 0.f);
             }
+            flipped = fl;
           }
           g = gsum16(g) + g0 + alpha * h0;
           h = gsum16(h) + h0;
           if (!lsdone) {
-            if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) lsdone = true;
+            if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
             else {
               if (g < 0.f) lo = alpha; else hi = alpha;
               float next = alpha - g / h;
@@ -845,6 +856,10 @@ struct HEnv {
           }
           if (__all_sync(kAll, lsdone)) break;
         }
+        // No row of this environment changed sides on [0, alpha] (rows are linear in alpha) and alpha minimises the
+        // cost along the Newton direction of exactly that active set: the new point is the solution, and the
+        // gradient pass that would confirm it is skipped.
+        exact = gballot(flipped) == 0 && lsconv && fabsf(alpha - 1.f) < 1e-3f;
       }
       bool moved = false;
       if (me && !done) {
@@ -859,7 +874,7 @@ struct HEnv {
       }
       __syncwarp();
       const unsigned movedbits = gballot(moved);
-      if (!constrained || movedbits == 0) done = true;
+      if (!constrained || movedbits == 0 || exact) done = true;
       if (__all_sync(kAll, done)) break;
     }
     __syncwarp();
@@ -878,20 +893,26 @@ struct HEnv {
     if (badacc) f = 0.f;
     const float v = me ? W_(L.o_qvel + lane) : 0.f;
     float av = 0.f, aa = 0.f;
+    bool badstate = false;  // mj_checkPos / mj_checkVel of the state this step ends in (stage 3 only)
     if (me) {
       av = W_(L.o_accv + lane) + B * v; aa = W_(L.o_acca + lane) + B * f;
       W_(L.o_accv + lane) = av; W_(L.o_acca + lane) = aa;
       W_(L.o_dir + lane) = (i == 3) ? av : v;  // the velocity that moves the positions (o_dir is free after the solve)
-      W_(L.o_qvel + lane) = W_(L.o_v0 + lane) + hstep * A * ((i == 3) ? aa : f);
+      const float vnew = W_(L.o_v0 + lane) + hstep * A * ((i == 3) ? aa : f);
+      W_(L.o_qvel + lane) = vnew;
+      badstate = !(fabsf(vnew) < kMaxVal);
     }
-    if (badacc && lane == 0) IW(L.o_cnt + TN_BAD) = 1;
     __syncwarp();
 #pragma unroll 1
     for (int j = lane; j < L.nj; j += 16) {
       const int qa = m->jnt_qadr[j], d = m->jnt_dadr[j];
       if (m->jnt_type[j] == MMZ_JNT_FREE) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) W_(L.o_qpos + qa + k) = W_(L.o_q0 + qa + k) + hstep * A * W_(L.o_dir + d + k);
+        for (int k = 0; k < 3; k++) {
+          const float pk = W_(L.o_q0 + qa + k) + hstep * A * W_(L.o_dir + d + k);
+          W_(L.o_qpos + qa + k) = pk;
+          badstate |= !(fabsf(pk) < kMaxVal);
+        }
         float wv[3] = {A * W_(L.o_dir + d + 3), A * W_(L.o_dir + d + 4), A * W_(L.o_dir + d + 5)};
         float q[4] = {W_(L.o_q0 + qa + 3), W_(L.o_q0 + qa + 4), W_(L.o_q0 + qa + 5), W_(L.o_q0 + qa + 6)};
         const float nw = norm3(wv), ang = hstep * nw;
@@ -905,22 +926,28 @@ struct HEnv {
           for (int k = 0; k < 4; k++) q[k] = q2[k];
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) W_(L.o_qpos + qa + 3 + k) = q[k];
+        for (int k = 0; k < 4; k++) { W_(L.o_qpos + qa + 3 + k) = q[k]; badstate |= !(fabsf(q[k]) < kMaxVal); }
       } else {
-        W_(L.o_qpos + qa) = W_(L.o_q0 + qa) + hstep * A * W_(L.o_dir + d);
+        const float pk = W_(L.o_q0 + qa) + hstep * A * W_(L.o_dir + d);
+        W_(L.o_qpos + qa) = pk;
+        badstate |= !(fabsf(pk) < kMaxVal);
       }
     }
+    // the flag of this mj_step: assigned by stage 0 (every warp read the previous step's flag long before), or-ed later
+    const bool flag = badacc || (i == 3 && gballot(badstate) != 0);
+    if (lane == 0 && (i == 0 || flag)) IW(L.o_cnt + TN_BAD) = flag ? 1 : 0;
     __syncwarp();
   }
 
   // ------------------------------------------------------------------ mj_forward
   MMZ_DI void forward(const TLayout& L, bool warmstart, int rk_stage = -1) {
-    // A: tree levels (kinematics, motion axes, world inertia, RNE forward)
+    // A: the kinematic trees (kinematics, motion axes, world inertia, RNE forward): the roots, one barrier, then
+    // every warp walks the subtrees of its level-1 bodies without further barriers
+    for (int i = wid; i < dv->lvl_off[1]; i += TW) body_pass(L, dv->lvl_body[i]);
+    __syncthreads();
 #pragma unroll 1
-    for (int lvl = 0; lvl < L.nlev; lvl++) {
-      for (int i = dv->lvl_off[lvl] + wid; i < dv->lvl_off[lvl + 1]; i += TW) body_pass(L, dv->lvl_body[i]);
-      __syncthreads();
-    }
+    for (int i = dv->chain_off[wid]; i < dv->chain_off[wid + 1]; i++) body_pass(L, dv->chain_body[i]);
+    __syncthreads();
     // B: geom poses, composite inertias, subtree forces
     if (wid == TW - 1) I(L.o_cnt + TN_OVERFLOW) = 0;
     {
@@ -975,31 +1002,31 @@ struct HEnv {
     for (int i = 0; i < L.nv; i++) bad |= !(fabsf(S(L.o_qvel + i)) < kMaxVal);
     return bad;
   }
-  MMZ_DI void park(const TLayout& L, bool on) {  // qpos0, zero velocity and acceleration
-    if (on) {
-      for (int i = wid; i < L.nq; i += TW) S(L.o_qpos + i) = m->qpos0[i];
-      for (int d = wid; d < L.nv; d += TW) { S(L.o_qvel + d) = 0.f; S(L.o_qacc + d) = 0.f; }
-    }
-  }
 
   // ------------------------------------------------------------------ mj_step, RK4 (mj_RungeKutta)
   // `dead`: the environment already blew up in this env-step; it is parked at qpos0 and keeps running.
-  MMZ_DI bool mj_step(const TLayout& L, bool dead) {
-    const float h = m->timestep;
+  // `bad`: the state is not finite (the caller's state_bad before the first step, then the flag the previous step's
+  // stage updates left) or the environment already blew up in this env-step: it is parked at qpos0 and keeps running.
+  // No thread may still be reading the state when this is entered (the caller's barrier / the post-solve barrier).
+  MMZ_DI bool mj_step(const TLayout& L, bool bad) {
     const int nq = L.nq, nv = L.nv;
-    bool bad = dead || state_bad(L);
+    for (int i = wid; i < nq; i += TW) {
+      const float q = bad ? m->qpos0[i] : S(L.o_qpos + i);
+      if (bad) S(L.o_qpos + i) = q;
+      S(L.o_q0 + i) = q;
+    }
+    for (int d = wid; d < nv; d += TW) {
+      const float v = bad ? 0.f : S(L.o_qvel + d);
+      if (bad) { S(L.o_qvel + d) = 0.f; S(L.o_qacc + d) = 0.f; }
+      S(L.o_v0 + d) = v; S(L.o_accv + d) = 0.f; S(L.o_acca + d) = 0.f;
+    }
     __syncthreads();
-    park(L, bad);
-    __syncthreads();
-    for (int i = wid; i < nq; i += TW) S(L.o_q0 + i) = S(L.o_qpos + i);
-    for (int d = wid; d < nv; d += TW) { S(L.o_v0 + d) = S(L.o_qvel + d); S(L.o_accv + d) = 0.f; S(L.o_acca + d) = 0.f; }
-    __syncthreads();
-    if (wid == 0) I(L.o_cnt + TN_BAD) = 0;
 #pragma unroll 1
     for (int i = 0; i < 4; i++) forward(L, true, i);  // each evaluation ends with its RK4 stage update (rk_update_g)
-    bad |= I(L.o_cnt + TN_BAD) != 0;  // a non-finite acceleration in some stage
-    // derived arrays (xpos, contacts) deliberately stay at the 4th-stage state: SURVEY quirk Q15
-    return bad || state_bad(L);
+    // a non-finite acceleration in some stage, or a non-finite state after the last one (written by rk_update_g before
+    // the barrier that ends the evaluation). Derived arrays (xpos, contacts) deliberately stay at the 4th-stage
+    // state: SURVEY quirk Q15
+    return bad || I(L.o_cnt + TN_BAD) != 0;
   }
 #undef S
 #undef W_

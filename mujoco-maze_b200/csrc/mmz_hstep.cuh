@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
       for (int k = 0; k < 4; k++) cn[(L.o_cnt + TN_ITER_SUM + k) * HS + e] = 0;
     const float bx = S(L.o_qpos), by = S(L.o_qpos + 1);
     t += 1;
+    bool bad = T.state_bad(L);  // mj_checkPos / mj_checkVel of the incoming state
     __syncthreads();
-    bool bad = false;
 #pragma unroll 1
     for (int k = 0; k < T.m->frame_skip; k++) bad = T.mj_step(L, bad);
     // AntEnv.step / SwimmerEnv.step (ant.py:61-73, swimmer.py:37-47)
