@@ -658,30 +658,27 @@ struct HEnv {
   }
   // Lane i holds row i of the symmetric positive-definite H (NVP registers) and element i of the right-hand
   // side: Gaussian elimination without pivoting, pivot row broadcast by shuffles, then back substitution.
-  MMZ_DI float elim_solve(float (&h)[NVP], float rhs, int nv) const {
+  // Rows / columns beyond the model's nv are the identity with a zero right-hand side (the caller pads them), so
+  // they need no guard: their multipliers and solution entries are exactly zero.
+  MMZ_DI float elim_solve(float (&h)[NVP], float rhs) const {
     float invd = 1.f;
 #pragma unroll
     for (int j = 0; j < NVP; j++) {
-      if (j < nv) {
-        const float piv = fmaxf(__shfl_sync(kAll, h[j], j, 16), kMinVal);
-        float inv;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv));
-        inv = inv * (2.f - piv * inv);
-        const float rj = __shfl_sync(kAll, rhs, j, 16);
-        const float f = (lane > j) ? h[j] * inv : 0.f;
-        if (lane == j) invd = inv;
-        rhs -= f * rj;
+      const float piv = fmaxf(__shfl_sync(kAll, h[j], j, 16), kMinVal);
+      float inv;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv));  // 1 ulp: as good as the approximate division of the build
+      const float rj = __shfl_sync(kAll, rhs, j, 16);
+      const float f = (lane > j) ? h[j] * inv : 0.f;
+      if (lane == j) invd = inv;
+      rhs -= f * rj;
 #pragma unroll
-        for (int k = j + 1; k < NVP; k++) h[k] -= f * __shfl_sync(kAll, h[k], j, 16);
-      }
+      for (int k = j + 1; k < NVP; k++) h[k] -= f * __shfl_sync(kAll, h[k], j, 16);
     }
     float x = rhs;
 #pragma unroll
     for (int j = NVP - 1; j >= 0; j--) {
-      if (j < nv) {
-        const float xj = __shfl_sync(kAll, x * invd, j, 16);
-        x = (lane == j) ? xj : ((lane < j) ? x - h[j] * xj : x);
-      }
+      const float xj = __shfl_sync(kAll, x * invd, j, 16);
+      x = (lane == j) ? xj : ((lane < j) ? x - h[j] * xj : x);
     }
     return x;
   }
@@ -757,13 +754,14 @@ struct HEnv {
     }
     __syncwarp();
     bool done = false;
+    // (M qacc)[lane] and the magnitude of its terms: from scratch at the warm start, then updated with every step
+    float Ma = 0.f, Mabs = 0.f;
+#pragma unroll
+    for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_qacc + (k < nv ? k : 0)); Ma += t; Mabs += fabsf(t); }
 #pragma unroll 1
     for (int it = 0; it < kTMaxNewton; it++) {
-      float Ma = 0.f, mag = 0.f;
-#pragma unroll
-      for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_qacc + (k < nv ? k : 0)); Ma += t; mag += fabsf(t); }
       float grad = Ma - sm_, dadd = 0.f;
-      mag += fabsf(sm_);
+      float mag = Mabs + fabsf(sm_);
       float ljar[2];
 #pragma unroll
       for (int s = 0; s < 2; s++) {
@@ -804,19 +802,19 @@ struct HEnv {
         for (int k = 0; k < NVP; k++)
           hrow[k] += u0 * __shfl_sync(kAll, jn, k, 16) + u1 * __shfl_sync(kAll, jt1, k, 16) + u2 * __shfl_sync(kAll, jt2, k, 16);
       }
-      const float dr = elim_solve(hrow, me ? -grad : 0.f, nv);
+      const float dr = elim_solve(hrow, me ? -grad : 0.f);
       if (me && !done) W_(L.o_dir + lane) = dr;
       __syncwarp();
       float alpha = 1.f;
       int ls = 0;
       bool exact = false;
+      float md = 0.f;  // (M dir)[lane]
+#pragma unroll
+      for (int k = 0; k < NVP; k++) md += mrow[k] * W_(L.o_dir + (k < nv ? k : 0));
       if (__any_sync(kAll, constrained && !done)) {
         float dummy0 = 0.f, dummy1 = 0.f;
         contact_products(L, cd, dr, done ? 0 : ncon, ncw, 1, &dummy0, &dummy1);
         __syncwarp();
-        float md = 0.f;
-#pragma unroll
-        for (int k = 0; k < NVP; k++) md += mrow[k] * W_(L.o_dir + (k < nv ? k : 0));
         const float g0 = gsum16(me ? dr * (Ma - sm_) : 0.f), h0 = gsum16(me ? dr * md : 0.f);
         float lo = 0.f, hi = -1.f;
         bool lsdone = done || !constrained;
@@ -867,6 +865,8 @@ struct HEnv {
         moved = fabsf(st) > 2e-6f * fabsf(al) + 1e-6f;
         al += st;
         W_(L.o_qacc + lane) = al;
+        Ma += alpha * md;
+        Mabs = fmaxf(Mabs, fabsf(Ma));
       }
       if (lane == 0 && !done) {
         IW(L.o_cnt + TN_ITER) = it + 1; IW(L.o_cnt + TN_ITER_SUM) += 1; IW(L.o_cnt + TN_LS_SUM) += ls;
