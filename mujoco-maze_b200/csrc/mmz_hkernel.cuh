@@ -808,9 +808,9 @@ struct HEnv {
       float alpha = 1.f;
       int ls = 0;
       bool exact = false;
-      float md = 0.f;  // (M dir)[lane]
+      float md = 0.f, mdabs = 0.f;  // (M dir)[lane] and the magnitude of its terms
 #pragma unroll
-      for (int k = 0; k < NVP; k++) md += mrow[k] * W_(L.o_dir + (k < nv ? k : 0));
+      for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_dir + (k < nv ? k : 0)); md += t; mdabs += fabsf(t); }
       if (__any_sync(kAll, constrained && !done)) {
         float dummy0 = 0.f, dummy1 = 0.f;
         contact_products(L, cd, dr, done ? 0 : ncon, ncw, 1, &dummy0, &dummy1);
@@ -866,7 +866,7 @@ struct HEnv {
         al += st;
         W_(L.o_qacc + lane) = al;
         Ma += alpha * md;
-        Mabs = fmaxf(Mabs, fabsf(Ma));
+        Mabs += fabsf(alpha) * mdabs;  // triangle inequality: still an upper bound of the magnitude of the terms
       }
       if (lane == 0 && !done) {
         IW(L.o_cnt + TN_ITER) = it + 1; IW(L.o_cnt + TN_ITER_SUM) += 1; IW(L.o_cnt + TN_LS_SUM) += ls;
