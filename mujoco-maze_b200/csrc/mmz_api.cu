@@ -280,7 +280,8 @@ bool configure_h(mmz_env* h, int* rc) {
   int o = 0;
   auto take = [&](int n) { int r = o; o += n; return r; };
   L.o_cnt = take(TN_CNT);
-  L.o_qpos = take(L.nq); L.o_qvel = take(L.nv); L.o_qacc = take(L.nv); L.o_objpos = take(3 * L.nlatch > 0 ? 3 * L.nlatch : 1);
+  const int nvp = box ? 16 : 14;  // the solver reads qacc / dir up to the instance's padded nv (zero beyond nv)
+  L.o_qpos = take(L.nq); L.o_qvel = take(L.nv); L.o_qacc = take(nvp); L.o_objpos = take(3 * L.nlatch > 0 ? 3 * L.nlatch : 1);
   L.o_ctrl = take(L.nu > 0 ? L.nu : 1); L.o_act = take(L.nu > 0 ? L.nu : 1);
   L.o_q0 = take(L.nq); L.o_v0 = take(L.nv); L.o_accv = take(L.nv); L.o_acca = take(L.nv);
   L.o_xpos = take(3 * L.nb);
@@ -288,7 +289,7 @@ bool configure_h(mmz_env* h, int* rc) {
   L.o_cdof = take(6 * L.nv);
   L.o_vel = take(6 * L.nb);
   L.o_M = take(L.nv * L.ldm);
-  L.o_smooth = take(L.nv); L.o_dir = take(L.nv);
+  L.o_smooth = take(L.nv); L.o_dir = take(nvp);
   L.o_gcnt = take(nitems); L.o_obs = take(L.obs_core);
   // Last: the arrays that are dead once the mass matrix and the smooth forces exist (orientations, inertias, bias
   // accelerations and forces). The contact slots are written after that point and OVERLAY them, then run on.

@@ -657,9 +657,10 @@ struct HEnv {
     }
   }
   // Lane i holds row i of the symmetric positive-definite H (NVP registers) and element i of the right-hand
-  // side: Gaussian elimination without pivoting, pivot row broadcast by shuffles, then back substitution.
-  // Rows / columns beyond the model's nv are the identity with a zero right-hand side (the caller pads them), so
-  // they need no guard: their multipliers and solution entries are exactly zero.
+  // side. Gauss-Jordan without pivoting: step j clears column j in EVERY other row (the rows above the pivot cost
+  // nothing extra in a SIMD step, and there is no back substitution), the pivot row is broadcast by shuffles, and
+  // each lane keeps the reciprocal of its own pivot for the final scaling. Rows / columns beyond the model's nv
+  // are the identity with a zero right-hand side (the caller pads them): their multipliers are exactly zero.
   MMZ_DI float elim_solve(float (&h)[NVP], float rhs) const {
     float invd = 1.f;
 #pragma unroll
@@ -668,19 +669,14 @@ struct HEnv {
       float inv;
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv));  // 1 ulp: as good as the approximate division of the build
       const float rj = __shfl_sync(kAll, rhs, j, 16);
-      const float f = (lane > j) ? h[j] * inv : 0.f;
-      if (lane == j) invd = inv;
+      const bool own = lane == j;
+      const float f = own ? 0.f : h[j] * inv;
+      invd = own ? inv : invd;
       rhs -= f * rj;
 #pragma unroll
       for (int k = j + 1; k < NVP; k++) h[k] -= f * __shfl_sync(kAll, h[k], j, 16);
     }
-    float x = rhs;
-#pragma unroll
-    for (int j = NVP - 1; j >= 0; j--) {
-      const float xj = __shfl_sync(kAll, x * invd, j, 16);
-      x = (lane == j) ? xj : ((lane < j) ? x - h[j] * xj : x);
-    }
-    return x;
+    return rhs * invd;
   }
   // this lane's column of the contact-frame Jacobian of the contact block at slot offset cs
   MMZ_DI void contact_jac(int cs, const float (&cd)[6], float* jn, float* jt1, float* jt2) const {
@@ -757,7 +753,7 @@ struct HEnv {
     // (M qacc)[lane] and the magnitude of its terms: from scratch at the warm start, then updated with every step
     float Ma = 0.f, Mabs = 0.f;
 #pragma unroll
-    for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_qacc + (k < nv ? k : 0)); Ma += t; Mabs += fabsf(t); }
+    for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_qacc + k); Ma += t; Mabs += fabsf(t); }  // padded to NVP
 #pragma unroll 1
     for (int it = 0; it < kTMaxNewton; it++) {
       float grad = Ma - sm_, dadd = 0.f;
@@ -810,7 +806,7 @@ struct HEnv {
       bool exact = false;
       float md = 0.f, mdabs = 0.f;  // (M dir)[lane] and the magnitude of its terms
 #pragma unroll
-      for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_dir + (k < nv ? k : 0)); md += t; mdabs += fabsf(t); }
+      for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_dir + k); md += t; mdabs += fabsf(t); }
       if (__any_sync(kAll, constrained && !done)) {
         float dummy0 = 0.f, dummy1 = 0.f;
         contact_products(L, cd, dr, done ? 0 : ncon, ncw, 1, &dummy0, &dummy1);

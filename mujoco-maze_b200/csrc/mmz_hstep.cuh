@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
 #define S(i) ws[(i) * HS + e]
   // the mass matrix is only ever written on its (static) sparsity pattern: clear it once
   for (int i = wid; i < L.nv * L.ldm; i += TW) S(L.o_M + i) = 0.f;
+  for (int i = L.nv + wid; i < NVP; i += TW) { S(L.o_qacc + i) = 0.f; S(L.o_dir + i) = 0.f; }  // padding the solver reads
   // ---- state tile: every row is 32 consecutive environments = one 128-byte line per warp load
   if (MODE != TMODE_RESET || A.mask != nullptr) {
     for (int r = wid; r < L.nstate; r += TW) S(h_row_slot(L, r)) = A.state[(size_t)r * A.npad + env0 + e];
