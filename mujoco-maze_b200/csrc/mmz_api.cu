@@ -300,7 +300,8 @@ bool configure_h(mmz_env* h, int* rc) {
   L.model_bytes = round_up(round_up((int)sizeof(mmz_model), 16) + (int)sizeof(TDerived), 16);
   int dev_smem = 0;
   if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess) return false;
-  const int avail = (dev_smem - round_up(L.model_bytes, 128) - 256) / (HS * 4);  // slots per environment
+  const int static_smem = 256 + TE * 16 * 16;  // mbarrier + the Jacobian scratch of the Hessian build
+  const int avail = (dev_smem - round_up(L.model_bytes, 128) - static_smem) / (HS * 4);  // slots per environment
   if (avail < dead1) return false;
   int maxcon = (avail - dead0) / L.cstride;
   const int want = box ? std::min(40, 16 + 8 * nbox) : 24;

@@ -99,6 +99,7 @@ struct HEnv {
   const mmz_model* m;
   const TDerived* dv;
   float* sm;
+  float4* jsc;              // [32 environments][16 dofs] scratch: contact Jacobian columns during the Hessian build
   int e, wid;               // tree view: lane = environment e; warp wid takes items wid, wid + 16, ...
   int genv, lane, gshift;   // solver view: environment wid + 16 * (laneid / 16), lane = dof
   float limD[2], limA[2];   // this lane's joint-limit rows (solver view)
@@ -794,9 +795,16 @@ struct HEnv {
         const float wnn = D * (a0 + a1 + a2 + a3), wn1 = D * mu * (a0 - a1), wn2 = D * mu * (a2 - a3);
         const float w11 = D * mu * mu * (a0 + a1), w22 = D * mu * mu * (a2 + a3);
         const float u0 = wnn * jn + wn1 * jt1 + wn2 * jt2, u1 = wn1 * jn + w11 * jt1, u2 = wn2 * jn + w22 * jt2;
+        // every lane needs the Jacobian columns of all dofs: through a 16-byte scratch entry per (environment, dof),
+        // one vector load per dof instead of three shuffles
+        __syncwarp();
+        jsc[genv * 16 + lane] = make_float4(jn, jt1, jt2, 0.f);
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < NVP; k++)
-          hrow[k] += u0 * __shfl_sync(kAll, jn, k, 16) + u1 * __shfl_sync(kAll, jt1, k, 16) + u2 * __shfl_sync(kAll, jt2, k, 16);
+        for (int k = 0; k < NVP; k++) {
+          const float4 jk = jsc[genv * 16 + k];
+          hrow[k] += u0 * jk.x + u1 * jk.y + u2 * jk.z;
+        }
       }
       const float dr = elim_solve(hrow, me ? -grad : 0.f);
       if (me && !done) W_(L.o_dir + lane) = dr;

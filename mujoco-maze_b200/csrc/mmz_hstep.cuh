@@ -108,6 +108,7 @@ template <int NVP, int BOX, int MODE>
 __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant__ TArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;
+  __shared__ float4 jscratch[TE * 16];
   const TLayout& L = A.L;
   const int tid = threadIdx.x;
   const int env0 = blockIdx.x * TE;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
   T.m = reinterpret_cast<const mmz_model*>(smem);
   T.dv = reinterpret_cast<const TDerived*>(smem + ((sizeof(mmz_model) + 15) & ~15));
   T.sm = ws;
+  T.jsc = jscratch;
   T.e = tid % 32;
   T.wid = tid / 32;
   T.genv = T.wid + 16 * (T.e >> 4);
