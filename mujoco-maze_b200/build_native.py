@@ -16,8 +16,8 @@ LIB = os.path.join(HERE, "libmmz.so")
 # (lanes per env, padded nv, FEAT bits: 1 box geoms, 2 fluid, 4 sphere pairs between moving bodies) - keep in step with MMZ_INSTANCES in csrc/mmz_api.cu
 INSTANCES = ((8, 4, 1), (8, 4, 7), (8, 8, 2), (8, 8, 7), (16, 14, 0), (16, 16, 1), (16, 16, 7), (32, 20, 7))
 # Division and square root use the approximate (2 ulp) instructions and denormals flush to zero: +3 % on the Ant step,
-# errors against the fp64 oracle unchanged (profiles/r1_parity.md). The transcendental functions (sincosf, powf, logf)
-# stay precise: -use_fast_math buys another 1.4 % but triples the median velocity error.
+# errors against the fp64 oracle unchanged (profiles/r1_parity.md). powf / logf stay precise: -use_fast_math buys
+# another 1.4 % but triples the median velocity error; only the joint-angle sine / cosine use the SFU (mmz_math.cuh).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-prec-div=false", "-prec-sqrt=false", "-ftz=true", *os.environ.get("MMZ_NVCC_EXTRA", "").split(),
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
