@@ -572,6 +572,7 @@ struct HEnv {
     if (x >= 1.f) return d1;
     if (x <= 0.f) return d0;
     if (power == 1.f) y = x;
+    else if (power == 2.f) y = x <= mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);  // MuJoCo's default power
     else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.f);
     else y = 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
     return d0 + y * (d1 - d0);
