@@ -263,6 +263,16 @@ bool configure_h(mmz_env* h, int* rc) {
       if (pair && t != MMZ_GEOM_BOX && m.geom_type[g2] != MMZ_GEOM_BOX) return false;
     }
   }
+  // the subtree sums walk [b, sub_end[b]): the bodies must be in depth-first order (MJCF order is)
+  for (int b = 0; b < m.nbody; b++) {
+    bool in_run = true;
+    for (int c = b + 1; c < m.nbody; c++) {
+      bool desc = false;
+      for (int a = c; a >= 0; a = m.body_parent[a]) desc |= a == b;
+      if (desc && !in_run) return false;
+      if (!desc) in_run = false;
+    }
+  }
   const bool box = nbox > 0;
   if (box && m.nv <= 14) return false;   // instances built: <14, no boxes> and <16, boxes>
   if (!box && m.nv > 14) return false;
@@ -354,6 +364,12 @@ void make_tderived(const mmz_model& m, TDerived* d) {
     }
     d->chain_off[TW] = n;
   }
+  for (int b = 0; b < m.nbody; b++) {
+    int e = b + 1;
+    while (e < m.nbody && (d->anc[e] >> b & 1)) e++;
+    d->sub_end[b] = e;
+  }
+  for (int k = 0; k < m.nu; k++) d->dof_act[m.act_dof[k]] |= 1 << k;
   d->ident[0] = d->ident[4] = d->ident[8] = 1.f;
   for (int g = 0; g < MMZ_MAXGEOM; g++) d->boxord[g] = -1;
   for (int g = 0; g < m.ngeom; g++)

@@ -50,6 +50,8 @@ struct TDerived {               // appended to the model blob in device memory
   // warp k % TW, parents first, so a chain needs no block barrier (lane e of one warp reads what it wrote)
   int32_t chain_off[TW + 1];
   int32_t chain_body[MMZ_MAXBODY];
+  int32_t sub_end[MMZ_MAXBODY];  // bodies are in depth-first order: the subtree of b is [b, sub_end[b])
+  int32_t dof_act[MMZ_MAXDOF];   // actuators driving dof d: bit k set for actuator k
   int32_t pad2[3];
   float ident[9];
   float padf[3];
@@ -308,9 +310,8 @@ struct HEnv {
     float acc[10];
     for (int k = 0; k < n; k++) acc[k] = S(src + n * b + k);
 #pragma unroll 1
-    for (int c = b + 1; c < L.nb; c++)
-      if (dv->anc[c] >> b & 1)
-        for (int k = 0; k < n; k++) acc[k] += S(src + n * c + k);
+    for (int c = b + 1; c < dv->sub_end[b]; c++)
+      for (int k = 0; k < n; k++) acc[k] += S(src + n * c + k);
     for (int k = 0; k < n; k++) S(dst + n * b + k) = acc[k];
   }
 
@@ -345,12 +346,12 @@ struct HEnv {
     const float passive = -m->dof_damping[d] * S(L.o_qvel + d);
     float act = 0.f;
 #pragma unroll 1
-    for (int k = 0; k < L.nu; k++)
-      if (m->act_dof[k] == d) {
-        float c = S(L.o_ctrl + k);
-        if (m->act_limited[k]) c = fminf(fmaxf(c, m->act_ctrlrange[k][0]), m->act_ctrlrange[k][1]);
-        act += m->act_gear[k] * c;
-      }
+    for (int bits = dv->dof_act[d]; bits; bits &= bits - 1) {
+      const int k = __ffs(bits) - 1;
+      float c = S(L.o_ctrl + k);
+      if (m->act_limited[k]) c = fminf(fmaxf(c, m->act_ctrlrange[k][0]), m->act_ctrlrange[k][1]);
+      act += m->act_gear[k] * c;
+    }
     S(L.o_smooth + d) = passive - bias + act;
   }
 
