@@ -886,32 +886,24 @@ struct Env {
   // of the right-hand side. Gaussian elimination without pivoting, the pivot row broadcast by
   // shuffles, then back substitution on the frozen upper rows: no shared memory, no barriers.
   // Rows >= nv are identity padding. Returns x = H^-1 rhs (element `lane`).
-  MMZ_DI float elim_solve(float (&h)[NVP], float rhs, int nv) const {
+  // Gauss-Jordan, as in the hybrid kernel (mmz_hkernel.cuh: elim_solve): step j clears column j in every other row,
+  // no back substitution; rows / columns beyond nv are the identity with a zero right-hand side (padded by the caller).
+  MMZ_DI float elim_solve(float (&h)[NVP], float rhs) const {
     float invd = 1.f;
 #pragma unroll
     for (int j = 0; j < NVP; j++) {
-      if (j < nv) {
-        const float piv = fmaxf(__shfl_sync(kFull, h[j], j, G), kMinVal);
-        float inv;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv));
-        inv = inv * (2.f - piv * inv);
-        const float rj = __shfl_sync(kFull, rhs, j, G);
-        const float f = (lane > j) ? h[j] * inv : 0.f;
-        if (lane == j) invd = inv;
-        rhs -= f * rj;
+      const float piv = fmaxf(__shfl_sync(kFull, h[j], j, G), kMinVal);
+      float inv;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv));
+      const float rj = __shfl_sync(kFull, rhs, j, G);
+      const bool own = lane == j;
+      const float f = own ? 0.f : h[j] * inv;
+      invd = own ? inv : invd;
+      rhs -= f * rj;
 #pragma unroll
-        for (int k = j + 1; k < NVP; k++) h[k] -= f * __shfl_sync(kFull, h[k], j, G);
-      }
+      for (int k = j + 1; k < NVP; k++) h[k] -= f * __shfl_sync(kFull, h[k], j, G);
     }
-    float x = rhs;
-#pragma unroll
-    for (int j = NVP - 1; j >= 0; j--) {
-      if (j < nv) {
-        const float xj = __shfl_sync(kFull, x * invd, j, G);
-        x = (lane == j) ? xj : ((lane < j) ? x - h[j] * xj : x);
-      }
-    }
-    return x;
+    return rhs * invd;
   }
 
   // this lane's column of the contact-frame Jacobian of contact block cs: (J_n, J_t1, J_t2)[lane]
@@ -1047,13 +1039,14 @@ struct Env {
           hrow[k] += u0 * __shfl_sync(kFull, jn, k, G) + u1 * __shfl_sync(kFull, jt1, k, G) + u2 * __shfl_sync(kFull, jt2, k, G);
       }
       MMZ_CONV(12);
-      const float dr = elim_solve(hrow, me ? -grad : 0.f, nv);
+      const float dr = elim_solve(hrow, me ? -grad : 0.f);
       MMZ_CONV(13);
       if (me && !done) dir[lane] = dr;
       sync();
       // ---- exact line search along dir: root of the monotone piecewise-linear derivative
       float alpha = 1.f;
       int ls = 0;
+      bool exact = false;
       if (__any_sync(kFull, constrained && !done)) {
         float dummy0 = 0.f, dummy1 = 0.f;
         contact_products(L, cd, dr, done ? 0 : ncon, ncw, 1, &dummy0, &dummy1);
@@ -1066,26 +1059,31 @@ struct Env {
         const float g0 = gsum<G>(me ? dr * (Ma - sm) : 0.f), h0 = gsum<G>(me ? dr * md : 0.f);
         float lo = 0.f, hi = -1.f;
         bool lsdone = done || !constrained;
+        bool flipped = true, lsconv = false;  // did a row change sides between 0 and alpha; did the search converge
 #pragma unroll 1
         for (int k = 0; k < kMaxLineSearch; k++) {
           float g = 0.f, h = 0.f;
+          bool fl = false;
 #pragma unroll
           for (int s = 0; s < 2; s++) {  // this lane's limit rows: jv = +-dr
             const float jv = s == 0 ? dr : -dr, x = ljar[s] + alpha * jv;
             if (limD[s] > 0.f && x < 0.f) { g += limD[s] * x * jv; h += limD[s] * jv * jv; }
+            fl |= limD[s] > 0.f && (x < 0.f) != (ljar[s] < 0.f);
           }
           if (!lsdone) {
 #pragma unroll 1
             for (int r = lane; r < 4 * ncon; r += G) {
               const float* cs = con + (r >> 2) * L.cstride;
-              const float jv = cs[C_JV + (r & 3)], x = cs[C_JAR + (r & 3)] + alpha * jv, D = cs[C_D];
+              const float jv = cs[C_JV + (r & 3)], jar = cs[C_JAR + (r & 3)], x = jar + alpha * jv, D = cs[C_D];
               if (x < 0.f) { g += D * x * jv; h += D * jv * jv; }
+              fl |= (x < 0.f) != (jar < 0.f);
             }
+            flipped = fl;
           }
           g = gsum<G>(g) + g0 + alpha * h0;
           h = gsum<G>(h) + h0;
           if (!lsdone) {
-            if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) lsdone = true;
+            if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
             else {
               if (g < 0.f) lo = alpha; else hi = alpha;
               float next = alpha - g / h;
@@ -1097,6 +1095,9 @@ struct Env {
           }
           if (__all_sync(kFull, lsdone)) break;
         }
+        // no row changed sides on [0, alpha] and alpha is the full Newton step: the new point is the solution of
+        // this active set, the gradient pass that would confirm it is skipped (as in the hybrid kernel)
+        exact = gballot(flipped) == 0 && lsconv && fabsf(alpha - 1.f) < 1e-3f;
       }
       bool moved = false;
       if (me && !done) {
@@ -1110,7 +1111,7 @@ struct Env {
       // unconstrained: one Newton step on the quadratic is exact. Otherwise stop at the fp32 floor,
       // when the step no longer changes any component of the iterate.
       const unsigned movedbits = gballot(moved);
-      if (!constrained || movedbits == 0) done = true;
+      if (!constrained || movedbits == 0 || exact) done = true;
       if (__all_sync(kFull, done)) break;
     }
     sync();
