@@ -595,7 +595,9 @@ int mmz_step_host(mmz_handle h, const float* h_action, float* h_obs, float* h_re
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = h->n;
-  if (!h->d_action) {
+  if (!h->d_done) {  // d_done is allocated last: a staging set that failed half-way is rebuilt
+    cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_info);
+    h->d_action = h->d_obs = h->d_reward = h->d_info = nullptr;
     CUDA_TRY(cudaMalloc(&h->d_action, n * (h->hm.nu > 0 ? h->hm.nu : 1) * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->d_obs, n * h->hm.obs_dim * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->d_reward, n * sizeof(float)));
