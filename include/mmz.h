@@ -98,7 +98,10 @@ int mmz_step(mmz_handle h, const float* d_action, float* d_obs, float* d_reward,
 
 /* Same step through HOST buffers: H2D of the actions, the kernel, D2H of
  * obs/reward/done/info, then a stream synchronise. This is the end-to-end
- * call a host-resident caller (the reference's numpy world) makes. */
+ * call a host-resident caller (the reference's numpy world) makes. Batches of
+ * 64 blocks or more run as 4 block ranges on internal streams so that the
+ * copies of one range overlap the kernel of another; results are identical
+ * to mmz_step (environments are independent). */
 int mmz_step_host(mmz_handle h, const float* h_action, float* h_obs, float* h_reward, uint8_t* h_done, float* h_info,
                   void* stream);
 

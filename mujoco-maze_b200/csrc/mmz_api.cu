@@ -76,6 +76,9 @@ struct mmz_env {
   // staging for mmz_step_host
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_info = nullptr;
   uint8_t* d_done = nullptr;
+  // mmz_step_host pipeline: block ranges of the batch on their own streams (copies of one range under the kernel of another)
+  cudaStream_t hs[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t hev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   unsigned long long seed = 0;
   unsigned long long launches = 0;
   int32_t* d_step_diag = nullptr;  // caller-owned, optional
@@ -203,7 +206,7 @@ int launch_view(mmz_env* h, int mode, const KArgs& A, cudaStream_t s) {
   return MMZ_OK;
 }
 
-int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s) {
+int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s, int block0 = 0, int nblocks = 0) {
   if (h->use_t) {
     TArgs T;
     memset(&T, 0, sizeof T);
@@ -213,7 +216,8 @@ int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s) {
     T.action = A.action; T.obs = A.obs; T.reward = A.reward; T.done = A.done; T.info = A.info;
     T.qacc_out = A.qacc_out; T.diag = A.diag; T.mask = A.mask; T.seed = A.seed;
     T.flags = h->flags; T.env_offset = h->env_offset; T.tol = h->tol;
-    h->tfn[mode]<<<h->npad / TE, TW * 32, h->smem_bytes, s>>>(T);
+    T.block0 = block0;
+    h->tfn[mode]<<<nblocks > 0 ? nblocks : h->npad / TE, TW * 32, h->smem_bytes, s>>>(T);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return launch_view(h, mode, A, s);
@@ -227,7 +231,8 @@ int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s) {
   A.flags = h->flags | (h->bsync << 8);
   A.env_offset = h->env_offset;
   int epb = h->tpb / h->G;
-  int blocks = (h->npad + epb - 1) / epb;  // padding environments run too (warp-uniform control flow)
+  int blocks = nblocks > 0 ? nblocks : (h->npad + epb - 1) / epb;  // padding environments run too (warp-uniform control flow)
+  A.block0 = block0;
   h->fn[mode]<<<blocks, h->tpb, h->smem_bytes, s>>>(A);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -604,6 +609,45 @@ int mmz_step_host(mmz_handle h, const float* h_action, float* h_obs, float* h_re
     CUDA_TRY(cudaMalloc(&h->d_info, n * 4 * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->d_done, n));
   }
+  // Large batches run as up to 4 block ranges on internal streams: the action upload and the result download of one
+  // range overlap the kernel of another. Ranges are whole blocks, every environment is stepped exactly once, and the
+  // result is identical to the single launch (environments are independent).
+  const int epb = h->use_t ? TE : h->tpb / h->G;
+  const int nblk = (h->npad + epb - 1) / epb;
+  const int nchunk = (h->hm.view_dim || nblk < 64) ? 1 : 4;
+  if (nchunk > 1) {
+    for (int c = 0; c < 4; c++)
+      if (!h->hs[c]) CUDA_TRY(cudaStreamCreateWithFlags(&h->hs[c], cudaStreamNonBlocking));
+    for (int c = 0; c < 5; c++)
+      if (!h->hev[c]) CUDA_TRY(cudaEventCreateWithFlags(&h->hev[c], cudaEventDisableTiming));
+    const size_t nu = h->hm.nu, od = h->hm.obs_dim;
+    CUDA_TRY(cudaEventRecord(h->hev[4], s));  // work already queued on the caller's stream comes first
+    for (int c = 0; c < nchunk; c++) {
+      const int b0 = (int)((long long)nblk * c / nchunk), b1 = (int)((long long)nblk * (c + 1) / nchunk);
+      const size_t e0 = (size_t)b0 * epb, e1 = std::min((size_t)b1 * epb, n);
+      cudaStream_t cs = h->hs[c];
+      CUDA_TRY(cudaStreamWaitEvent(cs, h->hev[4], 0));
+      if (e1 > e0 && nu)
+        CUDA_TRY(cudaMemcpyAsync(h->d_action + e0 * nu, h_action + e0 * nu, (e1 - e0) * nu * sizeof(float), cudaMemcpyHostToDevice, cs));
+      KArgs A;
+      memset(&A, 0, sizeof A);
+      A.action = h->d_action; A.obs = h->d_obs; A.reward = h->d_reward; A.done = h->d_done; A.info = h_info ? h->d_info : nullptr;
+      A.seed = h->seed;
+      A.diag = h->d_step_diag;
+      int rc = launch(h, MODE_STEP, A, cs, b0, b1 - b0);
+      if (rc != MMZ_OK) return rc;
+      if (e1 > e0) {
+        CUDA_TRY(cudaMemcpyAsync(h_obs + e0 * od, h->d_obs + e0 * od, (e1 - e0) * od * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(h_reward + e0, h->d_reward + e0, (e1 - e0) * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(h_done + e0, h->d_done + e0, e1 - e0, cudaMemcpyDeviceToHost, cs));
+        if (h_info) CUDA_TRY(cudaMemcpyAsync(h_info + e0 * 4, h->d_info + e0 * 4, (e1 - e0) * 4 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+      }
+      CUDA_TRY(cudaEventRecord(h->hev[c], cs));
+      CUDA_TRY(cudaStreamWaitEvent(s, h->hev[c], 0));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return MMZ_OK;
+  }
   CUDA_TRY(cudaMemcpyAsync(h->d_action, h_action, n * h->hm.nu * sizeof(float), cudaMemcpyHostToDevice, s));
   int rc = mmz_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, h_info ? h->d_info : nullptr, stream);
   if (rc != MMZ_OK) return rc;
@@ -703,6 +747,8 @@ void mmz_destroy(mmz_handle h) {
   cudaDeviceSynchronize();
   cudaFree(h->d_model); cudaFree(h->d_state); cudaFree(h->d_counters);
   cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_info); cudaFree(h->d_done);
+  for (cudaStream_t st : h->hs) if (st) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : h->hev) if (ev) cudaEventDestroy(ev);
   delete h;
 }
 

@@ -85,6 +85,7 @@ struct TArgs {
   const uint8_t* mask; // TMODE_RESET
   unsigned long long seed;
   unsigned flags;
+  int block0;          // first block of this launch (mmz_step_host pipelines block ranges)
   int env_offset;
   float tol;           // Newton convergence: |grad_d| <= tol * (magnitude of the terms grad_d is the sum of)
 };

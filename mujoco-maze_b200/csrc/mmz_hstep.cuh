@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
   __shared__ float4 jscratch[TE * 16];
   const TLayout& L = A.L;
   const int tid = threadIdx.x;
-  const int env0 = blockIdx.x * TE;
+  const int env0 = (A.block0 + blockIdx.x) * TE;
   float* ws = reinterpret_cast<float*>(smem + ((L.model_bytes + 127) & ~127));
 
   // ---- model constants: one bulk async copy global -> shared, completion on an mbarrier

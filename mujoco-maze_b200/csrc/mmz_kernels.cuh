@@ -39,6 +39,7 @@ struct KArgs {
   unsigned long long seed;
   unsigned flags;
   int env_offset;       // global index of env 0 (keeps the Philox streams independent of the sharding)
+  int block0;           // first block of this launch: mmz_step_host runs the batch as a few pipelined block ranges
 };
 
 MMZ_DI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -292,7 +293,7 @@ maze_kernel(const __grid_constant__ KArgs A) {
   __shared__ __align__(8) unsigned long long bar;
   const Layout& L = A.L;
   const int tid = threadIdx.x, epb = blockDim.x / G;
-  const int env0 = blockIdx.x * epb;
+  const int env0 = (A.block0 + blockIdx.x) * epb;
   float* wsbase = reinterpret_cast<float*>(smem + ((L.model_bytes + 127) & ~127));
 
   // ---- model constants: one bulk async copy global -> shared, completion on an mbarrier

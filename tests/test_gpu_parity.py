@@ -244,19 +244,22 @@ def test_point_wall_clamp_matches_reference_goldens(torch_cuda):
     print(report)
 
 
-def test_step_host_equals_device_step(torch_cuda):
+@pytest.mark.parametrize("env_id,n", [("AntUMaze-v0", 96), ("AntUMaze-v0", 2500), ("PointUMaze-v0", 5000)])
+def test_step_host_equals_device_step(env_id, n, torch_cuda):
+    """mmz_step_host == mmz_step bit for bit; from 64 blocks on the host call runs as 4 pipelined block ranges
+    (uploads / downloads of one range under the kernel of another), with a ragged last block."""
     from mujoco_maze.backend import BatchedSim
 
     torch = torch_cuda
-    model = make_model("AntUMaze-v0")
-    n = 96
+    model = make_model(env_id)
     rng = np.random.default_rng(5)
-    q, v = sample_states(model, "AntUMaze-v0", n, rng)
+    q, v = sample_states(model, env_id, n, rng)
     a = sample_actions(model, n, rng).astype(np.float32)
     s1, s2 = BatchedSim(model, n), BatchedSim(model, n)
     for s in (s1, s2):
         s.set_state(q, v, np.zeros(n, dtype=np.int32))
     obs, rew, done, info = s1.step(a)
+    launches0 = s2.launch_count
     h_a = torch.from_numpy(a).pin_memory()
     h_obs = torch.empty((n, s2.obs_dim), dtype=torch.float32).pin_memory()
     h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
@@ -266,6 +269,10 @@ def test_step_host_equals_device_step(torch_cuda):
     torch.cuda.synchronize()
     assert torch.equal(obs.cpu(), h_obs) and torch.equal(rew.cpu(), h_rew)
     assert torch.equal(done.cpu(), h_done) and torch.equal(info.cpu(), h_info)
+    assert s2.launch_count - launches0 == (1 if n < 1000 else 4)
+    q1, v1, t1 = s1.get_state()
+    q2, v2, t2 = s2.get_state()
+    assert torch.equal(q1, q2) and torch.equal(v1, v2) and torch.equal(t1, t2)
 
 
 def test_state_roundtrip_and_layouts(torch_cuda):
