@@ -356,18 +356,37 @@ void make_tderived(const mmz_model& m, TDerived* d) {
   }
   d->lvl_off[nlev] = k;
   {
-    int owner[MMZ_MAXBODY], nl1 = 0, n = 0;
+    // Tree walk roles. With enough warps every chain (the subtree of a level-1 body) gets a PAIR of warps from the top
+    // of the block (kinematic halves / dynamic halves, named barrier 1 + chain), and the roots' warps (0..nroots-1) do
+    // the roots' dynamic halves after the block barrier; otherwise chain c is walked whole by warp c % TW.
+    int nroots = 0, nl1 = 0;
+    for (int b = 0; b < m.nbody; b++) { nroots += m.body_level[b] == 0; nl1 += m.body_level[b] == 1; }
+    const bool pairs = nroots + 2 * nl1 <= TW && nl1 <= 14 && nl1 > 0;
+    int chain[MMZ_MAXBODY], c1 = 0;
     for (int b = 0; b < m.nbody; b++) {  // parents come first in the blob
-      owner[b] = -1;
-      if (m.body_level[b] == 1) owner[b] = nl1++ % TW;
-      else if (m.body_level[b] > 1) owner[b] = owner[m.body_parent[b]];
+      chain[b] = -1;
+      if (m.body_level[b] == 1) chain[b] = c1++;
+      else if (m.body_level[b] > 1) chain[b] = chain[m.body_parent[b]];
     }
+    auto chain_of_warp = [&](int w, int* kind, int* bar) {
+      *kind = A_IDLE; *bar = 0;
+      if (!pairs) { *kind = A_BOTH; return w; }  // warp w walks chains w, w + TW, ... whole
+      const int k = TW - 1 - w;                   // warps TW-1, TW-2: chain 0; TW-3, TW-4: chain 1; ...
+      if (k < 2 * nl1) { *kind = (k & 1) ? A_PAIR_DYN : A_PAIR_KIN; *bar = 1 + k / 2; return k / 2; }
+      if (w < nroots) *kind = A_ROOTDYN;
+      return -1;
+    };
+    int n = 0;
     for (int w = 0; w < TW; w++) {
+      int kind, bar;
+      const int c = chain_of_warp(w, &kind, &bar);
+      d->walk_kind[w] = kind; d->walk_bar[w] = bar;
       d->chain_off[w] = n;
       for (int b = 0; b < m.nbody; b++)
-        if (owner[b] == w) d->chain_body[n++] = b;
+        if (chain[b] >= 0 && (pairs ? chain[b] == c : chain[b] % TW == c)) d->chain_body[n++] = b;
     }
     d->chain_off[TW] = n;
+    d->walk_root_count = pairs ? 32 * (std::min(nroots, (int)TW) + nl1) : 0;
   }
   for (int b = 0; b < m.nbody; b++) {
     int e = b + 1;

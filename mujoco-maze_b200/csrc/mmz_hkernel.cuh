@@ -27,6 +27,8 @@ constexpr int TW = 16;  // warps per block
 constexpr int TE = 32;  // environments per block
 constexpr unsigned kAll = 0xffffffffu;
 constexpr int kTMaxNewton = 24;
+// roles of a warp in the tree walk (TDerived::walk_kind)
+enum { A_IDLE = 0, A_KIN = 1, A_PAIR_KIN = 2, A_PAIR_DYN = 3, A_ROOTDYN = 4, A_BOTH = 5 };
 constexpr int kTMaxLineSearch = 24;
 
 enum { TMODE_STEP = 0, TMODE_FORWARD = 1, TMODE_OBSERVE = 2, TMODE_RESET = 3, TMODE_REFRESH = 4 };
@@ -49,7 +51,12 @@ struct TDerived {               // appended to the model blob in device memory
   // bodies below the roots, grouped by the warp that walks them: the subtree of the k-th level-1 body belongs to
   // warp k % TW, parents first, so a chain needs no block barrier (lane e of one warp reads what it wrote)
   int32_t chain_off[TW + 1];
-  int32_t chain_body[MMZ_MAXBODY];
+  int32_t chain_body[2 * MMZ_MAXBODY];  // (a chain appears twice when a pair of warps walks it)
+  // role of warp w in the tree walk after the roots' kinematics (A_* below), its named barrier, and how many
+  // threads meet at the barrier that publishes the roots' dynamic halves
+  int32_t walk_kind[TW];
+  int32_t walk_bar[TW];
+  int32_t walk_root_count;
   int32_t sub_end[MMZ_MAXBODY];  // bodies are in depth-first order: the subtree of b is [b, sub_end[b])
   int32_t dof_act[MMZ_MAXDOF];   // actuators driving dof d: bit k set for actuator k
   int32_t pad2[3];
@@ -118,9 +125,9 @@ struct HEnv {
     r[0] = S(L.o_qpos); r[1] = S(L.o_qpos + 1); r[2] = (m->jnt_type[0] == MMZ_JNT_FREE) ? S(L.o_qpos + 2) : 0.f;
   }
 
-  // ------------------------------------------------------------------ phase A: one body of a tree level
-  // kinematics (mj_kinematics), its motion axes, its world spatial inertia and the forward pass of RNE
-  MMZ_DI void body_pass(const TLayout& L, int b) {
+  // ------------------------------------------------------------------ phase A: one body, in two halves
+  // kinematic half: mj_kinematics of the body and its motion axes (reads the parent's pose)
+  MMZ_DI void body_kin(const TLayout& L, int b) {
     const int p = m->body_parent[b];
     float pos[3], quat[4], R[9], rf[3];
     ref(L, rf);
@@ -207,6 +214,19 @@ struct HEnv {
         for (int i = 0; i < 3; i++) { S(L.o_cdof + 6 * (freed + 3 + k) + i) = ax[i]; S(L.o_cdof + 6 * (freed + 3 + k) + 3 + i) = lin[i]; }
       }
     }
+  }
+  // dynamic half: world spatial inertia and the forward pass of RNE (reads its own pose and the parent's velocity /
+  // bias acceleration)
+  MMZ_DI void body_dyn(const TLayout& L, int b) {
+    const int p = m->body_parent[b];
+    float pos[3], quat[4], R[9], rf[3];
+    ref(L, rf);
+#pragma unroll
+    for (int k = 0; k < 3; k++) pos[k] = S(L.o_xpos + 3 * b + k);
+#pragma unroll
+    for (int k = 0; k < 4; k++) quat[k] = S(L.o_xquat + 4 * b + k);
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = S(L.o_xmat + 9 * b + k);
     const int d0 = m->body_dofadr[b], d1 = d0 + m->body_dofnum[b];
 
     // ---- world spatial inertia about the reference point
@@ -279,7 +299,7 @@ struct HEnv {
   MMZ_DI void kinematics_only(const TLayout& L) {
 #pragma unroll 1
     for (int lvl = 0; lvl < L.nlev; lvl++) {
-      for (int i = dv->lvl_off[lvl] + wid; i < dv->lvl_off[lvl + 1]; i += TW) body_pass(L, dv->lvl_body[i]);
+      for (int i = dv->lvl_off[lvl] + wid; i < dv->lvl_off[lvl + 1]; i += TW) body_kin(L, dv->lvl_body[i]);
       __syncthreads();
     }
   }
@@ -635,6 +655,10 @@ struct HEnv {
     S(o + C_AREF + 3) = -bb * (jv0 - mu * jv2) - kr;
   }
 
+  // named barriers among a subset of the block's warps (ids 1..15; 0 is __syncthreads)
+  MMZ_DI static void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+  MMZ_DI static void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
   // ================================================================== solver view (16 lanes = one environment)
   MMZ_DI unsigned gballot(bool p) const { return (__ballot_sync(kAll, p) >> gshift) & 0xffffu; }
   MMZ_DI static float gsum16(float v) {
@@ -948,13 +972,35 @@ struct HEnv {
 
   // ------------------------------------------------------------------ mj_forward
   MMZ_DI void forward(const TLayout& L, bool warmstart, int rk_stage = -1) {
-    // A: the kinematic trees (kinematics, motion axes, world inertia, RNE forward): the roots, one barrier, then
-    // every warp walks the subtrees of its level-1 bodies without further barriers
-    for (int i = wid; i < dv->lvl_off[1]; i += TW) body_pass(L, dv->lvl_body[i]);
-    __syncthreads();
+    // A: the kinematic trees. Pass 0: the kinematic half of the roots. Pass 1: the subtree of every level-1 body is
+    // walked by a PAIR of warps - one does the kinematic halves down the chain, its partner follows one body behind
+    // with the dynamic halves (named barrier per pair) - while the roots' warps do the roots' dynamic halves and
+    // publish them through one more named barrier. The critical path is 3 kinematic + 1 dynamic half instead of 3
+    // full body passes, and the torso's dynamic half overlaps the legs' kinematics. (Models with more chains than
+    // warp pairs walk every chain in one warp: A_BOTH.)
+    {
+      const int kind1 = dv->walk_kind[wid], bar = dv->walk_bar[wid];
 #pragma unroll 1
-    for (int i = dv->chain_off[wid]; i < dv->chain_off[wid + 1]; i++) body_pass(L, dv->chain_body[i]);
-    __syncthreads();
+      for (int pass = 0; pass < 2; pass++) {
+        const bool legacy = dv->walk_root_count == 0;
+        const int kind = pass == 0 ? (legacy ? A_BOTH : A_KIN) : kind1;
+        const int32_t* list = (pass == 0 || kind == A_ROOTDYN) ? dv->lvl_body : dv->chain_body;
+        const bool roots = pass == 0 || kind == A_ROOTDYN;
+        const int i0 = roots ? wid : dv->chain_off[wid], i1 = roots ? dv->lvl_off[1] : dv->chain_off[wid + 1];
+        if (kind != A_IDLE) {
+#pragma unroll 1
+          for (int i = i0; i < i1; i += roots ? TW : 1) {
+            const int b = list[i];
+            if (kind == A_KIN || kind == A_PAIR_KIN || kind == A_BOTH) body_kin(L, b);
+            if (kind == A_PAIR_KIN || kind == A_PAIR_DYN) named_sync(bar, 64);
+            if (kind == A_PAIR_DYN && i == i0) named_sync(15, dv->walk_root_count);  // the roots' velocities exist
+            if (kind != A_KIN && kind != A_PAIR_KIN) body_dyn(L, b);
+          }
+          if (kind == A_ROOTDYN) named_arrive(15, dv->walk_root_count);
+        }
+        __syncthreads();
+      }
+    }
     // B: geom poses, composite inertias, subtree forces
     if (wid == TW - 1) I(L.o_cnt + TN_OVERFLOW) = 0;
     {
