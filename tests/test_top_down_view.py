@@ -58,6 +58,22 @@ def test_oracle_view_matches_reference(key, oracle_lib):
         np.testing.assert_allclose(obs[core: core + 75], s["view"], rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize("key", ["GoalRewardUMaze-point", "GoalRewardPush-point"])
+def test_view_is_agent_independent(key, oracle_lib):
+    """The reference method only reads the maze, the scaling and two body positions: the same goldens hold for a
+    Swimmer in that maze (torso = its first body, x / y = its first two slide joints)."""
+    from mujoco_maze.swimmer import SwimmerEnv
+
+    case = G["cases"][CASES.index(key)]
+    model = compile_maze_model(SwimmerEnv, view_task(case["task"], case["scaling"]), case["scaling"])
+    assert model.names["body"][int(model.obj_body[int(model.nobj)])] == "torso"
+    o = oracle_lib.OracleEnv(model)
+    core = int(model.obs_dim) - 76
+    for s in case["samples"][:8]:
+        o.set_state(state_for(model, s["robot"], s["blocks"]), np.zeros(int(model.nv)), t=0)
+        np.testing.assert_allclose(o.observe()[core: core + 75], s["view"], rtol=0, atol=1e-9)
+
+
 def test_view_is_off_for_every_registered_task():
     # maze_task.py:68 - no upstream task overrides TOP_DOWN_VIEW, so registered ids never pay for the view
     for maze_id in T.TaskRegistry.keys():
