@@ -79,3 +79,27 @@ def test_view_is_off_for_every_registered_task():
     for maze_id in T.TaskRegistry.keys():
         for cls in T.TaskRegistry.tasks(maze_id):
             assert cls.TOP_DOWN_VIEW is False
+
+
+def test_env_with_view_has_reference_obs_shape_and_no_cpu_fallback():
+    """MazeEnv of a TOP_DOWN_VIEW task: obs = state part + 75 view entries + t (maze_env.py:368-369); without CUDA the
+    view accessor fails loudly like every other product path."""
+    import torch
+
+    from mujoco_maze import maze_env
+    from mujoco_maze.backend import MmzError
+
+    cls = type("PushView", (T.GoalRewardPush,), dict(TOP_DOWN_VIEW=True))
+    env = maze_env.MazeEnv(PointEnv, cls, maze_size_scaling=4.0)
+    plain = maze_env.MazeEnv(PointEnv, T.GoalRewardPush, maze_size_scaling=4.0)
+    assert env.observation_space.shape == (plain.observation_space.shape[0] + 75,)
+    assert env.has_extended_obs
+    with pytest.raises(ValueError):
+        plain.get_top_down_view()
+    if not torch.cuda.is_available():
+        with pytest.raises(MmzError):
+            env.get_top_down_view()
+        with pytest.raises(MmzError):
+            env.render(mode="rgb_array")
+    with pytest.raises(NotImplementedError):
+        env.render(mode="human")
