@@ -277,6 +277,10 @@ class MazeEnv(gym.Env):
         return (torch.as_tensor(r, dtype=torch.float32, device=reward.device),
                 torch.as_tensor(d, dtype=torch.uint8, device=done.device))
 
+    def set_marker(self) -> None:
+        """Reference maze_env.py:384-387 moves the goal sites of the MuJoCo scene before rendering. The rasteriser draws
+        the goal discs straight from the compiled task goals, so there is nothing to move; kept for API parity."""
+
     def render(self, mode="rgb_array", width: int = 256, height: int = 256, env_ids: Any = None, **kwargs) -> Any:
         """Top-down RGB image(s) from the batched CUDA rasteriser (`mmz_render`).
 
