@@ -292,39 +292,73 @@ bool configure_h(mmz_env* h, int* rc) {
   L.cstride = C_STRIDE;
   L.nstate = m.nq + 2 * m.nv + 3 * L.nlatch;
   const int nitems = L.ng + nbox * (1 + 2 * 9 + (nbox - 1));  // HEnv::n_items
+  const int nvp = box ? 16 : 14;  // the solver reads qacc / dir up to the instance's padded nv (zero beyond nv)
+  L.model_bytes = round_up(round_up((int)sizeof(mmz_model), 16) + (int)sizeof(TDerived), 16);
+  int dev_smem = 0;
+  if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess) return false;
   int o = 0;
   auto take = [&](int n) { int r = o; o += n; return r; };
   L.o_cnt = take(TN_CNT);
-  const int nvp = box ? 16 : 14;  // the solver reads qacc / dir up to the instance's padded nv (zero beyond nv)
   L.o_qpos = take(L.nq); L.o_qvel = take(L.nv); L.o_qacc = take(nvp); L.o_objpos = take(3 * L.nlatch > 0 ? 3 * L.nlatch : 1);
   L.o_ctrl = take(L.nu > 0 ? L.nu : 1); L.o_act = take(L.nu > 0 ? L.nu : 1);
   L.o_q0 = take(L.nq); L.o_v0 = take(L.nv); L.o_accv = take(L.nv); L.o_acca = take(L.nv);
   L.o_xpos = take(3 * L.nb);
-  L.o_gpos = take(3 * L.ng); L.o_gax = take(3 * L.ng); L.o_gmat = take(nbox > 0 ? 9 * nbox : 1);
-  L.o_cdof = take(6 * L.nv);
-  L.o_vel = take(6 * L.nb);
-  L.o_M = take(L.nv * L.ldm);
-  L.o_smooth = take(L.nv); L.o_dir = take(nvp);
-  L.o_gcnt = take(nitems); L.o_obs = take(L.obs_core);
-  // Last: the arrays that are dead once the mass matrix and the smooth forces exist (orientations, inertias, bias
-  // accelerations and forces). The contact slots are written after that point and OVERLAY them, then run on.
-  const int dead0 = o;
-  L.o_xquat = take(4 * L.nb); L.o_xmat = take(9 * L.nb); L.o_iw = take(10 * L.nb);
-  L.o_ic = take(10 * L.nb); L.o_acc = take(6 * L.nb); L.o_frc = take(6 * L.nb); L.o_fsub = take(6 * L.nb);
-  const int dead1 = o;
-  L.model_bytes = round_up(round_up((int)sizeof(mmz_model), 16) + (int)sizeof(TDerived), 16);
-  int dev_smem = 0;
-  if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess) return false;
-  const int static_smem = 256 + TE * 16 * 16;  // mbarrier + the Jacobian scratch of the Hessian build
-  const int avail = (dev_smem - round_up(L.model_bytes, 128) - static_smem) / (HS * 4);  // slots per environment
-  if (avail < dead1) return false;
-  int maxcon = (avail - dead0) / L.cstride;
-  const int want = box ? std::min(40, 16 + 8 * nbox) : 24;
-  if (maxcon > want) maxcon = want;
-  if (maxcon < (box ? 24 : 16)) return false;  // does not fit: use the lanes-per-environment kernel
-  L.maxcon = maxcon;
-  L.o_con = dead0;
-  L.nslots = std::max(dead1, dead0 + maxcon * L.cstride);
+  if (!box) {
+    // Solver v2. In front: what stays live while the solver iterates. Then everything that is dead by then - the
+    // solver view loads the mass matrix, the smooth forces and the motion axes into registers and passes a block
+    // barrier first - and the stored contact Jacobian and the per-contact forces / weights OVERLAY it (natural
+    // [environment][contact] order, float4). The contact records come last.
+    L.v2 = 1;
+    L.cstride = K_STRIDE;
+    L.o_dir = take(nvp);
+    L.o_nat = o = round_up(o, 4);  // 4 slots = 528 bytes: the float4 areas start 16-byte aligned
+    L.o_cdof = take(6 * L.nv);
+    L.o_M = take(L.nv * L.ldm);
+    L.o_smooth = take(L.nv);
+    L.o_obs = take(L.obs_core);
+    L.o_gpos = take(3 * L.ng); L.o_gax = take(3 * L.ng); L.o_gmat = take(1);
+    L.o_vel = take(6 * L.nb);
+    L.o_gcnt = take(nitems);
+    L.o_xquat = take(4 * L.nb); L.o_xmat = take(9 * L.nb); L.o_iw = take(10 * L.nb);
+    L.o_ic = take(10 * L.nb); L.o_acc = take(6 * L.nb); L.o_frc = take(6 * L.nb); L.o_fsub = take(6 * L.nb);
+    const int dead1 = o;
+    const int static_smem = 256;  // mbarrier
+    const int avail = (dev_smem - round_up(L.model_bytes, 128) - static_smem) / (HS * 4);  // slots per environment
+    int maxcon = 16;  // one lane per contact in the contact passes
+    for (; maxcon >= 10; maxcon--) {
+      L.jes = maxcon * (nvp + 1);
+      L.fa_off = TE * L.jes + 1;
+      const int nat_bytes = (L.fa_off + TE * 2 * maxcon) * 16;
+      L.o_con = std::max(dead1, L.o_nat + (nat_bytes + HS * 4 - 1) / (HS * 4));
+      L.nslots = L.o_con + maxcon * L.cstride;
+      if (L.nslots <= avail) break;
+    }
+    if (maxcon < 10) return false;  // does not fit: use the lanes-per-environment kernel
+    L.maxcon = maxcon;
+  } else {
+    L.o_gpos = take(3 * L.ng); L.o_gax = take(3 * L.ng); L.o_gmat = take(nbox > 0 ? 9 * nbox : 1);
+    L.o_cdof = take(6 * L.nv);
+    L.o_vel = take(6 * L.nb);
+    L.o_M = take(L.nv * L.ldm);
+    L.o_smooth = take(L.nv); L.o_dir = take(nvp);
+    L.o_gcnt = take(nitems); L.o_obs = take(L.obs_core);
+    // Last: the arrays that are dead once the mass matrix and the smooth forces exist (orientations, inertias, bias
+    // accelerations and forces). The contact slots are written after that point and OVERLAY them, then run on.
+    const int dead0 = o;
+    L.o_xquat = take(4 * L.nb); L.o_xmat = take(9 * L.nb); L.o_iw = take(10 * L.nb);
+    L.o_ic = take(10 * L.nb); L.o_acc = take(6 * L.nb); L.o_frc = take(6 * L.nb); L.o_fsub = take(6 * L.nb);
+    const int dead1 = o;
+    const int static_smem = 256 + TE * 16 * 16;  // mbarrier + the Jacobian scratch of the Hessian build
+    const int avail = (dev_smem - round_up(L.model_bytes, 128) - static_smem) / (HS * 4);  // slots per environment
+    if (avail < dead1) return false;
+    int maxcon = (avail - dead0) / L.cstride;
+    const int want = std::min(40, 16 + 8 * nbox);
+    if (maxcon > want) maxcon = want;
+    if (maxcon < 24) return false;  // does not fit: use the lanes-per-environment kernel
+    L.maxcon = maxcon;
+    L.o_con = dead0;
+    L.nslots = std::max(dead1, dead0 + maxcon * L.cstride);
+  }
   h->TL = L;
   h->smem_bytes = round_up(L.model_bytes, 128) + L.nslots * HS * 4;
   for (int mode = 0; mode < 5; mode++) {
@@ -394,6 +428,8 @@ void make_tderived(const mmz_model& m, TDerived* d) {
     d->sub_end[b] = e;
   }
   for (int k = 0; k < m.nu; k++) d->dof_act[m.act_dof[k]] |= 1 << k;
+  for (int i = 0; i < m.nv; i++)
+    for (int j = i; j >= 0; j = m.dof_parent[j]) { d->dof_rel[i] |= 1 << j; d->dof_rel[j] |= 1 << i; }
   d->ident[0] = d->ident[4] = d->ident[8] = 1.f;
   for (int g = 0; g < MMZ_MAXGEOM; g++) d->boxord[g] = -1;
   for (int g = 0; g < m.ngeom; g++)

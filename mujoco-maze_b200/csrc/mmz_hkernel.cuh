@@ -59,6 +59,7 @@ struct TDerived {               // appended to the model blob in device memory
   int32_t walk_root_count;
   int32_t sub_end[MMZ_MAXBODY];  // bodies are in depth-first order: the subtree of b is [b, sub_end[b])
   int32_t dof_act[MMZ_MAXDOF];   // actuators driving dof d: bit k set for actuator k
+  int32_t dof_rel[MMZ_MAXDOF];   // bit k set: dof k is d, an ancestor or a descendant of d (the sparsity pattern of row d of M)
   int32_t pad2[3];
   float ident[9];
   float padf[3];
@@ -74,6 +75,10 @@ struct TLayout {
   int o_iw, o_ic, o_vel, o_acc, o_frc, o_fsub;
   int o_M, o_smooth, o_dir;
   int o_con, o_cnt, o_gcnt, o_obs, o_act;
+  // solver v2 (models without box geoms): the stored contact Jacobian and the per-contact forces / Hessian weights, as
+  // float4 arrays in natural [environment][contact] order. They OVERLAY the slots [o_nat, o_con) of the [slot][33]
+  // workspace, whose arrays are all dead while the solver runs.
+  int v2, o_nat, jes, fa_off;  // first slot (multiple of 4); float4s per environment of the Jacobian area; float4 offset of FA
 };
 
 struct TArgs {
@@ -100,16 +105,28 @@ struct TArgs {
 
 constexpr int HS = 33;  // row stride of the [slot][33] workspace
 
+// Contact record of solver v2 (floats; mmz_layout.h C_* is the record of the first solver). The narrow phase leaves
+// point, normal, first tangent (the second is their cross product), distance, the inverse weight, the two bodies and
+// the two geoms (the mixed solref / solimp / margin / friction are re-derived from those); the constraint rows then
+// replace bodies by signed dof masks and the temporaries by (mu, D, aref[4]); once the Jacobian is stored, point and
+// frame are dead and J a - aref of the four pyramid rows takes their place.
+enum { K_POS = 0, K_N = 3, K_T1 = 6, K_BODY1 = 9, K_BODY2 = 10, K_MPOS = 9, K_MNEG = 10, K_MU = 11, K_D = 12, K_AREF = 13,
+       K_DIST = 13, K_INVW = 14, K_GEOM = 15, K_OTHER = 16, K_JAR = 0, K_STRIDE = 17 };
+static __device__ __noinline__ void write_contact_record2(float* c, const RawContact& rc, int b1, int b2, float iw, int g, int other);
+
 // one out-of-line copy of the record writer (it has several call sites); `c` points at element (slot 0, env) of the
 // contact block, consecutive fields are HS floats apart
 static __device__ __noinline__ void write_contact_record(float* c, const RawContact& rc, int b1, int b2, float iw, const float* par);
 
 template <int NVP, int BOX>
 struct HEnv {
+  static constexpr bool V2 = BOX == 0;  // which solver (and contact record) the instance uses
   const mmz_model* m;
   const TDerived* dv;
   float* sm;
-  float4* jsc;              // [32 environments][16 dofs] scratch: contact Jacobian columns during the Hessian build
+  float4* jsc;              // [32 environments][16 dofs] scratch: contact Jacobian columns during the Hessian build (BOX)
+  float4* jg;               // solver v2: this lane's environment in the Jacobian area, [contact][NVP + 1] float4
+  float4* fg;               // solver v2: its per-contact (force, Hessian weights) pairs, [contact][2] float4
   int e, wid;               // tree view: lane = environment e; warp wid takes items wid, wid + 16, ...
   int genv, lane, gshift;   // solver view: environment wid + 16 * (laneid / 16), lane = dof
   float limD[2], limA[2];   // this lane's joint-limit rows (solver view)
@@ -405,9 +422,13 @@ struct HEnv {
   // stores a narrow-phase record into contact slot `slot` (layout C_* of mmz_layout.h); the normal points
   // from body b1 (geom1) to body b2 (geom2), -1 = world
   MMZ_DI void write_contact(const TLayout& L, int slot, const RawContact& rc, int b1, int b2, float iw, int g, int other) {
-    float par[9];
-    mix_params(g, other, par);
-    write_contact_record(sm + (L.o_con + slot * L.cstride) * HS + e, rc, b1, b2, iw, par);
+    if (V2) {
+      write_contact_record2(sm + (L.o_con + slot * L.cstride) * HS + e, rc, b1, b2, iw, g, other);
+    } else {
+      float par[9];
+      mix_params(g, other, par);
+      write_contact_record(sm + (L.o_con + slot * L.cstride) * HS + e, rc, b1, b2, iw, par);
+    }
   }
   // number of collision items: one per geom, then (BOX only) BCAND candidate slots per box geom
   static constexpr int BCELLS = 9;                       // maze cells a box geom can reach (3 x 3)
@@ -612,6 +633,48 @@ struct HEnv {
   }
   // contact slot c (tree view): narrow-phase record -> D, aref[4], signed dof masks, point relative to the
   // reference. J qvel is the point velocity of body2 minus body1, from the body velocities RNE has computed.
+  // the same for the record of solver v2
+  MMZ_DI void contact_rows2(const TLayout& L, int c) {
+    if (c >= I(L.o_cnt + TN_CON)) return;
+    const int o = L.o_con + c * L.cstride;
+    float rf[3], cp[3], fr[9], par[9], v[3] = {0.f, 0.f, 0.f};
+    ref(L, rf);
+#pragma unroll
+    for (int k = 0; k < 3; k++) cp[k] = S(o + K_POS + k) - rf[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) fr[k] = S(o + K_N + k);
+    cross3(fr + 6, fr, fr + 3);
+    const float dist = S(o + K_DIST), invw = S(o + K_INVW);
+    mix_params(__float_as_int(S(o + K_GEOM)), __float_as_int(S(o + K_OTHER)), par);
+    const float margin = par[0], mu = par[1];
+    const int b1 = __float_as_int(S(o + K_BODY1)), b2 = __float_as_int(S(o + K_BODY2));
+    const int mask1 = b1 >= 0 ? m->body_dofmask[b1] : 0, mask2 = b2 >= 0 ? m->body_dofmask[b2] : 0;
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+      const int b = side == 0 ? b2 : b1;
+      if (b < 0) continue;
+      float bv[6], wxp[3];
+#pragma unroll
+      for (int k = 0; k < 6; k++) bv[k] = S(L.o_vel + 6 * b + k);
+      cross3(wxp, bv, cp);
+      const float sg = side == 0 ? 1.f : -1.f;
+#pragma unroll
+      for (int k = 0; k < 3; k++) v[k] += sg * (bv[3 + k] + wxp[k]);
+    }
+    const float jv0 = dot3(fr, v), jv1 = dot3(fr + 3, v), jv2 = dot3(fr + 6, v);
+    float D, kr, bb;
+    row_params(par + 2, par + 4, dist, margin, invw * (1.f + mu * mu), &D, &kr, &bb);
+#pragma unroll
+    for (int k = 0; k < 3; k++) S(o + K_POS + k) = cp[k];
+    S(o + K_MPOS) = __int_as_float(mask2 & ~mask1);
+    S(o + K_MNEG) = __int_as_float(mask1 & ~mask2);
+    S(o + K_MU) = mu;
+    S(o + K_D) = 1.f / fmaxf(kMinVal, 2.f * mu * mu / D);  // all edges of the pyramid share R = 2 mu^2 R_first
+    S(o + K_AREF + 0) = -bb * (jv0 + mu * jv1) - kr;
+    S(o + K_AREF + 1) = -bb * (jv0 - mu * jv1) - kr;
+    S(o + K_AREF + 2) = -bb * (jv0 + mu * jv2) - kr;
+    S(o + K_AREF + 3) = -bb * (jv0 - mu * jv2) - kr;
+  }
   MMZ_DI void contact_rows(const TLayout& L, int c) {
     if (c >= I(L.o_cnt + TN_CON)) return;
     const int o = L.o_con + c * L.cstride;
@@ -911,6 +974,233 @@ struct HEnv {
     __syncwarp();
   }
 
+  // ================================================================== solver v2 (models without box geoms)
+  // The contact Jacobian is built ONCE per forward evaluation and kept in shared memory, one float4 per (contact, dof):
+  // (J_n, mu J_t1, mu J_t2, |J_n| + mu (|J_t1| + |J_t2|)). With the friction coefficient folded into the tangential
+  // columns the four pyramid rows of a contact are n + t1, n - t1, n + t2, n - t2. The passes over the CONTACTS then run
+  // with lane = contact (all contacts of an environment at once, no cross-lane reductions: J x is a loop over the dofs,
+  // the rows, their forces and Hessian weights stay in the lane), the passes over the DOFS (gradient J^T f, Hessian rows)
+  // with lane = dof read those results back. 3.3 k -> 1.9 k warp instructions per Newton iteration of a standing Ant.
+  MMZ_DI float4* jrow(int c) const { return jg + c * (NVP + 1); }
+
+  MMZ_DI void build_jac(const TLayout& L, const float (&cd)[6], int ncon, int ncw) {
+#pragma unroll 1
+    for (int c = 0; c < ncw; c++) {
+      const int cs = L.o_con + c * L.cstride;
+      const int mp = __float_as_int(W_(cs + K_MPOS)), mn = __float_as_int(W_(cs + K_MNEG));
+      const float s = (float)(mp >> lane & 1) - (float)(mn >> lane & 1);
+      float p[3], fr[9], wxp[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) p[k] = W_(cs + K_POS + k);
+#pragma unroll
+      for (int k = 0; k < 6; k++) fr[k] = W_(cs + K_N + k);
+      cross3(fr + 6, fr, fr + 3);
+      cross3(wxp, cd, p);
+      const float v[3] = {s * (cd[3] + wxp[0]), s * (cd[4] + wxp[1]), s * (cd[5] + wxp[2])};
+      const float mu = W_(cs + K_MU);
+      float jn = dot3(fr, v), jt1 = mu * dot3(fr + 3, v), jt2 = mu * dot3(fr + 6, v);
+      if (c >= ncon) { jn = 0.f; jt1 = 0.f; jt2 = 0.f; }  // the slot holds nothing for this environment (the other one of the warp has more contacts)
+      if (lane < NVP) jrow(c)[lane] = make_float4(jn, jt1, jt2, fabsf(jn) + fabsf(jt1) + fabsf(jt2));
+    }
+  }
+  // lane = contact, x = qacc: J x - aref per pyramid row (kept in the record for the line search), and for the dof passes
+  // the force of the active rows in (n, t1, t2) coordinates + the scale of its rounding error, and the Hessian weights
+  MMZ_DI void contact_pass_grad(const TLayout& L, int ncon, int ncw) {
+    const int c = lane;
+    if (c < ncw) {
+      float4 F = make_float4(0.f, 0.f, 0.f, 0.f), Wt = F;
+      if (c < ncon) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, sa = 0.f;
+        const float4* jr = jrow(c);
+#pragma unroll
+        for (int k = 0; k < NVP; k++) {
+          const float4 j = jr[k];
+          const float x = W_(L.o_qacc + k);
+          s0 = fmaf(j.x, x, s0); s1 = fmaf(j.y, x, s1); s2 = fmaf(j.z, x, s2); sa = fmaf(j.w, fabsf(x), sa);
+        }
+        const int cs = L.o_con + c * L.cstride;
+        const float r0 = W_(cs + K_AREF), r1 = W_(cs + K_AREF + 1), r2 = W_(cs + K_AREF + 2), r3 = W_(cs + K_AREF + 3);
+        const float D = W_(cs + K_D);
+        const float j0 = s0 + s1 - r0, j1 = s0 - s1 - r1, j2 = s0 + s2 - r2, j3 = s0 - s2 - r3;
+        W_(cs + K_JAR) = j0; W_(cs + K_JAR + 1) = j1; W_(cs + K_JAR + 2) = j2; W_(cs + K_JAR + 3) = j3;
+        const float a0 = j0 < 0.f, a1 = j1 < 0.f, a2 = j2 < 0.f, a3 = j3 < 0.f;
+        const float f0 = a0 * D * j0, f1 = a1 * D * j1, f2 = a2 * D * j2, f3 = a3 * D * j3;
+        const float bound = sa + fmaxf(fmaxf(fabsf(r0), fabsf(r1)), fmaxf(fabsf(r2), fabsf(r3)));
+        F = make_float4(f0 + f1 + f2 + f3, f0 - f1, f2 - f3, D * bound * (a0 + a1 + a2 + a3));
+        Wt = make_float4(D * (a0 - a1), D * (a2 - a3), D * (a0 + a1), D * (a2 + a3));
+      }
+      fg[2 * c] = F; fg[2 * c + 1] = Wt;
+    }
+  }
+  // Newton solver (mj_solNewton), same algorithm and stopping rules as solve_g
+  MMZ_DI void solve_g2(const TLayout& L, bool warmstart) {
+    const int nv = L.nv, ncon = IW(L.o_cnt + TN_CON);
+    const int ncw = max(ncon, __shfl_xor_sync(kAll, ncon, 16));  // the two environments of the warp
+    const bool me = lane < nv;
+    const unsigned limbits = gballot(limD[0] > 0.f || limD[1] > 0.f);
+    const bool constrained = ncon > 0 || limbits != 0;
+    float mrow[NVP];  // this lane's row of the mass matrix (zero outside its sparsity pattern and outside the model)
+    const int rel = me ? dv->dof_rel[lane] : 0;
+#pragma unroll
+    for (int k = 0; k < NVP; k++) mrow[k] = (rel >> k & 1) ? W_(L.o_M + lane * L.ldm + k) : 0.f;
+    const float sm_ = me ? W_(L.o_smooth + lane) : 0.f;
+    {
+      float cd[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) cd[k] = me ? W_(L.o_cdof + 6 * lane + k) : 0.f;
+      // The Jacobian area overlays the mass matrix, the motion axes and every other array the solver view has read by
+      // now (all environments of the block, in the other layout): no warp may write it before all warps are here.
+      __syncthreads();
+      build_jac(L, cd, ncon, ncw);
+    }
+    float al = (warmstart && me) ? W_(L.o_qacc + lane) : 0.f;
+    if (!(fabsf(al) < kMaxVal)) al = 0.f;  // a blown-up environment restarts from zero
+    if (me) W_(L.o_qacc + lane) = al;
+    const int nlim = __popc(gballot(limD[0] > 0.f)) + __popc(gballot(limD[1] > 0.f));
+    if (lane == 0) {
+      IW(L.o_cnt + TN_ITER) = 0; IW(L.o_cnt + TN_LIM) = nlim;
+      IW(L.o_cnt + TN_CON_MAX) = max(IW(L.o_cnt + TN_CON_MAX), ncon);
+    }
+    __syncwarp();
+    bool done = false;
+    float Ma = 0.f, Mabs = 0.f;  // (M qacc)[lane] and the magnitude of its terms, updated with every step
+#pragma unroll
+    for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_qacc + k); Ma += t; Mabs += fabsf(t); }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int it = 0; it < kTMaxNewton; it++) {
+      float grad = Ma - sm_, dadd = 0.f;
+      float mag = Mabs + fabsf(sm_);
+      float ljar[2];
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const float sign = s == 0 ? 1.f : -1.f;
+        ljar[s] = sign * al - limA[s];
+        if (limD[s] > 0.f && ljar[s] < 0.f) {
+          grad += limD[s] * ljar[s] * sign;
+          mag += limD[s] * (fabsf(al) + fabsf(limA[s]));
+          dadd += limD[s];
+        }
+      }
+      contact_pass_grad(L, ncon, ncw);
+      __syncwarp();
+#pragma unroll 1
+      for (int c = 0; c < ncw; c++) {
+        const float4 j = lane < NVP ? jrow(c)[lane] : zero4, F = fg[2 * c];
+        grad += j.x * F.x + j.y * F.y + j.z * F.z;
+        mag = fmaf(j.w, F.w, mag);
+      }
+      if (gballot(me && fabsf(grad) > tol * mag + 1e-30f) == 0) done = true;
+      if (__all_sync(kAll, done)) break;
+      float hrow[NVP];
+#pragma unroll
+      for (int k = 0; k < NVP; k++) {
+        const float mk = mrow[k];
+        hrow[k] = (k == lane) ? (me ? mk + dadd : 1.f) : mk;
+      }
+#pragma unroll 1
+      for (int c = 0; c < ncw; c++) {
+        const float4 Wt = fg[2 * c + 1];
+        const float wnn = Wt.z + Wt.w;
+        if (!__any_sync(kAll, wnn != 0.f)) continue;  // no active row in this contact, in either environment
+        const float4 j = lane < NVP ? jrow(c)[lane] : zero4;
+        const float u0 = wnn * j.x + Wt.x * j.y + Wt.y * j.z, u1 = Wt.x * j.x + Wt.z * j.y, u2 = Wt.y * j.x + Wt.w * j.z;
+        const float4* jr = jrow(c);
+#pragma unroll
+        for (int k = 0; k < NVP; k++) {
+          const float4 jk = jr[k];
+          hrow[k] += u0 * jk.x + u1 * jk.y + u2 * jk.z;
+        }
+      }
+      const float dr = elim_solve(hrow, me ? -grad : 0.f);
+      if (me && !done) W_(L.o_dir + lane) = dr;
+      __syncwarp();
+      float alpha = 1.f;
+      int ls = 0;
+      bool exact = false;
+      float md = 0.f, mdabs = 0.f;  // (M dir)[lane] and the magnitude of its terms
+#pragma unroll
+      for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_dir + k); md += t; mdabs += fabsf(t); }
+      if (__any_sync(kAll, constrained && !done)) {
+        // lane = contact: its four pyramid rows stay in registers for the whole line search
+        float cjar[4] = {1.f, 1.f, 1.f, 1.f}, cjv[4] = {0.f, 0.f, 0.f, 0.f}, cD = 0.f;
+        if (lane < ncon && !done) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+          const float4* jr = jrow(lane);
+#pragma unroll
+          for (int k = 0; k < NVP; k++) {
+            const float4 j = jr[k];
+            const float x = W_(L.o_dir + k);
+            s0 = fmaf(j.x, x, s0); s1 = fmaf(j.y, x, s1); s2 = fmaf(j.z, x, s2);
+          }
+          cjv[0] = s0 + s1; cjv[1] = s0 - s1; cjv[2] = s0 + s2; cjv[3] = s0 - s2;
+          const int cs = L.o_con + lane * L.cstride;
+#pragma unroll
+          for (int i = 0; i < 4; i++) cjar[i] = W_(cs + K_JAR + i);
+          cD = W_(cs + K_D);
+        }
+        const float g0 = gsum16(me ? dr * (Ma - sm_) : 0.f), h0 = gsum16(me ? dr * md : 0.f);
+        float lo = 0.f, hi = -1.f;
+        bool lsdone = done || !constrained;
+        bool flipped = true, lsconv = false;  // did a row change sides between 0 and alpha; did the search converge
+#pragma unroll 1
+        for (int k = 0; k < kTMaxLineSearch; k++) {
+          float g = 0.f, h = 0.f;
+          bool fl = false;
+#pragma unroll
+          for (int s = 0; s < 2; s++) {
+            const float jv = s == 0 ? dr : -dr, x = ljar[s] + alpha * jv;
+            if (limD[s] > 0.f && x < 0.f) { g += limD[s] * x * jv; h += limD[s] * jv * jv; }
+            fl |= limD[s] > 0.f && (x < 0.f) != (ljar[s] < 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float x = cjar[i] + alpha * cjv[i];
+            if (x < 0.f) { g += cD * x * cjv[i]; h += cD * cjv[i] * cjv[i]; }
+            fl |= (x < 0.f) != (cjar[i] < 0.f);
+          }
+          if (!lsdone) flipped = fl;
+          g = gsum16(g) + g0 + alpha * h0;
+          h = gsum16(h) + h0;
+          if (!lsdone) {
+            if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
+            else {
+              if (g < 0.f) lo = alpha; else hi = alpha;
+              float next = alpha - g / h;
+              if (hi >= 0.f && (next <= lo || next >= hi)) next = 0.5f * (lo + hi);
+              if (next <= lo && hi < 0.f) next = 2.f * alpha + 1e-6f;
+              if (next == alpha) lsdone = true;
+              else { alpha = next; ls++; }
+            }
+          }
+          if (__all_sync(kAll, lsdone)) break;
+        }
+        // No row of this environment changed sides on [0, alpha] (rows are linear in alpha) and alpha minimises the
+        // cost along the Newton direction of exactly that active set: the new point is the solution, and the
+        // gradient pass that would confirm it is skipped.
+        exact = gballot(flipped) == 0 && lsconv && fabsf(alpha - 1.f) < 1e-3f;
+      }
+      bool moved = false;
+      if (me && !done) {
+        const float st = alpha * dr;
+        moved = fabsf(st) > 2e-6f * fabsf(al) + 1e-6f;
+        al += st;
+        W_(L.o_qacc + lane) = al;
+        Ma += alpha * md;
+        Mabs += fabsf(alpha) * mdabs;  // triangle inequality: still an upper bound of the magnitude of the terms
+      }
+      if (lane == 0 && !done) {
+        IW(L.o_cnt + TN_ITER) = it + 1; IW(L.o_cnt + TN_ITER_SUM) += 1; IW(L.o_cnt + TN_LS_SUM) += ls;
+        if (it == kTMaxNewton - 1) IW(L.o_cnt + TN_CAPPED) += 1;
+      }
+      __syncwarp();
+      const unsigned movedbits = gballot(moved);
+      if (!constrained || movedbits == 0 || exact) done = true;
+      if (__all_sync(kAll, done)) break;
+    }
+    __syncwarp();
+  }
+
   // RK4 bookkeeping of stage i for this warp's two environments (solver view, lane = dof), right after their solve:
   // accumulate the stage (B weights), then move to the state of the next stage, or to the final combination after
   // stage 3 (classic tableau, A = 1/2, 1/2, 1). Positions integrate on the configuration manifold (mj_integratePos):
@@ -1036,12 +1326,16 @@ struct HEnv {
     // E: contact rows
     {
       const int ncmax = __reduce_max_sync(kAll, I(L.o_cnt + TN_CON));
-      for (int c = wid; c < ncmax; c += TW) contact_rows(L, c);
+      for (int c = wid; c < ncmax; c += TW) {
+        if (V2) contact_rows2(L, c);
+        else contact_rows(L, c);
+      }
     }
     __syncthreads();
     // solver view: warp w owns environments w and w + 16
     limit_rows_g(L);
-    solve_g(L, warmstart);
+    if (V2) solve_g2(L, warmstart);
+    else solve_g(L, warmstart);
     if (rk_stage >= 0) rk_update_g(L, rk_stage);  // in the shadow of the wait for the slowest solve of the block
     __syncthreads();
   }
@@ -1102,6 +1396,23 @@ static __device__ __noinline__ void write_contact_record(float* c, const RawCont
   c[C_INVW * HS] = iw;
   c[C_BODY1 * HS] = __int_as_float(b1);
   c[C_BODY2 * HS] = __int_as_float(b2);
+}
+
+static __device__ __noinline__ void write_contact_record2(float* c, const RawContact& rc, int b1, int b2, float iw, int g, int other) {
+  float fr[9];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { fr[k] = rc.normal[k]; fr[3 + k] = rc.hint[k]; }
+  make_frame(fr);
+#pragma unroll
+  for (int k = 0; k < 3; k++) c[(K_POS + k) * HS] = rc.pos[k];
+#pragma unroll
+  for (int k = 0; k < 6; k++) c[(K_N + k) * HS] = fr[k];
+  c[K_DIST * HS] = rc.dist;
+  c[K_INVW * HS] = iw;
+  c[K_BODY1 * HS] = __int_as_float(b1);
+  c[K_BODY2 * HS] = __int_as_float(b2);
+  c[K_GEOM * HS] = __int_as_float(g);
+  c[K_OTHER * HS] = __int_as_float(other);
 }
 
 }  // namespace mmz
