@@ -1122,8 +1122,19 @@ struct HEnv {
 #pragma unroll
       for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_dir + k); md += t; mdabs += fabsf(t); }
       if (__any_sync(kAll, constrained && !done)) {
-        // lane = contact: its four pyramid rows stay in registers for the whole line search
-        float cjar[4] = {1.f, 1.f, 1.f, 1.f}, cjv[4] = {0.f, 0.f, 0.f, 0.f}, cD = 0.f;
+        // This lane's rows - the two joint-limit rows of its dof and (lane = contact) the four pyramid rows of its contact -
+        // stay in registers for the whole search. While jar + alpha jv < 0 a row adds D (jar + alpha jv) jv = rb + alpha ra
+        // to the derivative along the direction and D jv^2 = ra to the curvature. Absent rows: jar = 1, the rest 0.
+        float rj[6], rv[6], ra[6], rb[6];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const float jv = s == 0 ? dr : -dr;
+          const bool on = limD[s] > 0.f;
+          rj[s] = on ? ljar[s] : 1.f; rv[s] = on ? jv : 0.f;
+          ra[s] = on ? limD[s] * jv * jv : 0.f; rb[s] = on ? limD[s] * ljar[s] * jv : 0.f;
+        }
+#pragma unroll
+        for (int i = 2; i < 6; i++) { rj[i] = 1.f; rv[i] = 0.f; ra[i] = 0.f; rb[i] = 0.f; }
         if (lane < ncon && !done) {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f;
           const float4* jr = jrow(lane);
@@ -1133,52 +1144,64 @@ struct HEnv {
             const float x = W_(L.o_dir + k);
             s0 = fmaf(j.x, x, s0); s1 = fmaf(j.y, x, s1); s2 = fmaf(j.z, x, s2);
           }
-          cjv[0] = s0 + s1; cjv[1] = s0 - s1; cjv[2] = s0 + s2; cjv[3] = s0 - s2;
+          rv[2] = s0 + s1; rv[3] = s0 - s1; rv[4] = s0 + s2; rv[5] = s0 - s2;
           const int cs = L.o_con + lane * L.cstride;
-#pragma unroll
-          for (int i = 0; i < 4; i++) cjar[i] = W_(cs + K_JAR + i);
-          cD = W_(cs + K_D);
-        }
-        const float g0 = gsum16(me ? dr * (Ma - sm_) : 0.f), h0 = gsum16(me ? dr * md : 0.f);
-        float lo = 0.f, hi = -1.f;
-        bool lsdone = done || !constrained;
-        bool flipped = true, lsconv = false;  // did a row change sides between 0 and alpha; did the search converge
-#pragma unroll 1
-        for (int k = 0; k < kTMaxLineSearch; k++) {
-          float g = 0.f, h = 0.f;
-          bool fl = false;
-#pragma unroll
-          for (int s = 0; s < 2; s++) {
-            const float jv = s == 0 ? dr : -dr, x = ljar[s] + alpha * jv;
-            if (limD[s] > 0.f && x < 0.f) { g += limD[s] * x * jv; h += limD[s] * jv * jv; }
-            fl |= limD[s] > 0.f && (x < 0.f) != (ljar[s] < 0.f);
-          }
+          const float cD = W_(cs + K_D);
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            const float x = cjar[i] + alpha * cjv[i];
-            if (x < 0.f) { g += cD * x * cjv[i]; h += cD * cjv[i] * cjv[i]; }
-            fl |= (x < 0.f) != (cjar[i] < 0.f);
+            rj[2 + i] = W_(cs + K_JAR + i);
+            ra[2 + i] = cD * rv[2 + i] * rv[2 + i]; rb[2 + i] = cD * rj[2 + i] * rv[2 + i];
           }
-          if (!lsdone) flipped = fl;
-          g = gsum16(g) + g0 + alpha * h0;
-          h = gsum16(h) + h0;
-          if (!lsdone) {
-            if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
-            else {
-              if (g < 0.f) lo = alpha; else hi = alpha;
-              float next = alpha - g / h;
-              if (hi >= 0.f && (next <= lo || next >= hi)) next = 0.5f * (lo + hi);
-              if (next <= lo && hi < 0.f) next = 2.f * alpha + 1e-6f;
-              if (next == alpha) lsdone = true;
-              else { alpha = next; ls++; }
-            }
-          }
-          if (__all_sync(kAll, lsdone)) break;
         }
-        // No row of this environment changed sides on [0, alpha] (rows are linear in alpha) and alpha minimises the
-        // cost along the Newton direction of exactly that active set: the new point is the solution, and the
-        // gradient pass that would confirm it is skipped.
-        exact = gballot(flipped) == 0 && lsconv && fabsf(alpha - 1.f) < 1e-3f;
+        bool lsdone = done || !constrained;
+        bool flipped = false, lsconv = false;  // did a row change sides between 0 and alpha; did the search converge
+        {
+          // The full Newton step crosses no row: the cost along the direction is ONE quadratic on [0, 1], whose minimiser
+          // is the Newton step itself. No search (and no rounding noise that could make it look unconverged).
+          bool fl = false;
+#pragma unroll
+          for (int r = 0; r < 6; r++) fl |= (rj[r] + rv[r] < 0.f) != (rj[r] < 0.f);
+          flipped = gballot(fl) != 0;
+          if (!flipped && !lsdone) { lsdone = true; lsconv = true; }
+        }
+        if (!__all_sync(kAll, lsdone)) {
+          const bool searched = !lsdone;
+          const float g0 = gsum16(me ? dr * (Ma - sm_) : 0.f), h0 = gsum16(me ? dr * md : 0.f);
+          float lo = 0.f, hi = -1.f;
+#pragma unroll 1
+          for (int k = 0; k < kTMaxLineSearch; k++) {
+            float g = 0.f, h = 0.f;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+              if (rj[r] + alpha * rv[r] < 0.f) { g += rb[r] + alpha * ra[r]; h += ra[r]; }
+            }
+            g = gsum16(g) + g0 + alpha * h0;
+            h = gsum16(h) + h0;
+            if (!lsdone) {
+              if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
+              else {
+                if (g < 0.f) lo = alpha; else hi = alpha;
+                float next = alpha - g / h;
+                if (hi >= 0.f && (next <= lo || next >= hi)) next = 0.5f * (lo + hi);
+                if (next <= lo && hi < 0.f) next = 2.f * alpha + 1e-6f;
+                if (next == alpha) lsdone = true;
+                else { alpha = next; ls++; }
+              }
+            }
+            if (__all_sync(kAll, lsdone)) break;
+          }
+          {  // rows are linear in alpha: compare the sides at the accepted step with those at 0
+            bool fl = false;
+#pragma unroll
+            for (int r = 0; r < 6; r++) fl |= (rj[r] + alpha * rv[r] < 0.f) != (rj[r] < 0.f);
+            const bool any = gballot(fl) != 0;  // (a vote: outside the per-environment condition)
+            if (searched) flipped = any;
+          }
+        }
+        // No row of this environment changed sides on [0, alpha] and alpha minimises the cost along the Newton direction
+        // of exactly that active set: the new point is the solution, and the gradient pass that would confirm it is
+        // skipped.
+        exact = !flipped && lsconv && fabsf(alpha - 1.f) < 1e-3f;
       }
       bool moved = false;
       if (me && !done) {
