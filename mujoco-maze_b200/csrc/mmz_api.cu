@@ -310,6 +310,11 @@ bool configure_h(mmz_env* h, int* rc) {
     // [environment][contact] order, float4). The contact records come last.
     L.v2 = 1;
     L.cstride = K_STRIDE;
+    {  // the Ant's dof tree: a free root and 2-dof chains hanging off its last dof
+      bool ant = m.nv == 14 && m.jnt_type[0] == MMZ_JNT_FREE;
+      for (int d = 0; d < m.nv && ant; d++) ant = m.dof_parent[d] == (d < 6 ? d - 1 : (d & 1) ? d - 1 : 5);
+      L.topo = ant ? 1 : 0;
+    }
     L.o_dir = take(nvp);
     L.o_nat = o = round_up(o, 4);  // 4 slots = 528 bytes: the float4 areas start 16-byte aligned
     L.o_cdof = take(6 * L.nv);

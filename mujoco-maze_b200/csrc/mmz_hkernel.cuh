@@ -79,6 +79,7 @@ struct TLayout {
   // float4 arrays in natural [environment][contact] order. They OVERLAY the slots [o_nat, o_con) of the [slot][33]
   // workspace, whose arrays are all dead while the solver runs.
   int v2, o_nat, jes, fa_off;  // first slot (multiple of 4); float4s per environment of the Jacobian area; float4 offset of FA
+  int topo;                    // 1: the dof tree is the Ant's (free root + 2-dof chains): sparse elimination order (elim_solve2)
 };
 
 struct TArgs {
@@ -104,6 +105,15 @@ struct TArgs {
 
 
 constexpr int HS = 33;  // row stride of the [slot][33] workspace
+
+#ifdef MMZ_PHASE_TIMING  // development aid (tools/build_debug.py): cycles per phase of block 0, Newton iterations per solve
+__device__ unsigned long long g_phase[16];
+__device__ unsigned g_iter_hist[16];
+__device__ unsigned long long g_wsolve[16], g_wwait[16];  // per warp of block 0: its own solve, its wait for the slowest
+#define MMZ_TICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_phase[i] += t_ - tick_; tick_ = t_; } } while (0)
+#else
+#define MMZ_TICK(i) do { } while (0)
+#endif
 
 // Contact record of solver v2 (floats; mmz_layout.h C_* is the record of the first solver). The narrow phase leaves
 // point, normal, first tangent (the second is their cross product), distance, the inverse weight, the two bodies and
@@ -437,15 +447,23 @@ struct HEnv {
   MMZ_DI int item_base(const TLayout& L, int item) const {
     int base = 0;
 #pragma unroll 1
-    for (int k = 0; k < item; k++) base += I(L.o_gcnt + k);
+    for (int k = 0; k < item; k++) base += I(L.o_gcnt + k) & 31;
     return base;
   }
   // Collision item `item`. pass 0 counts its contacts (into o_gcnt), pass 1 writes them at the slots following those
   // of the items before it: the contact order is the item order, independent of warp timing.
   //   item < ng: sphere / capsule geom against the floor plane, the maze boxes near it and the movable box geoms;
   //   item >= ng (BOX): candidate c of box geom k: the floor (plane-box corners), a maze box or a later box geom (box-box).
+  // Pass 0 also leaves, above the count (5 bits), which tests produced a contact: bit 5 + end for the floor, bits
+  // 7 + 2 cand (+ 1) for box candidate cand < 12, bit 31 = "a later candidate": pass 1 skips the whole item when no
+  // environment of the warp found anything, and otherwise repeats only the tests that hit in some environment.
   MMZ_DI void collide_item(const TLayout& L, int item, int pass) {
     int n = 0;
+    unsigned hits = 0, wanted = 0xffffffffu;
+    if (pass == 1 && item < L.ng) {
+      wanted = __reduce_or_sync(kAll, (unsigned)I(L.o_gcnt + item));
+      if ((wanted & 31u) == 0) return;
+    }
     const int base = pass == 1 ? item_base(L, item) : 0;
     if (item < L.ng) {
       const int g = item, type = m->geom_type[g];
@@ -470,6 +488,7 @@ struct HEnv {
           for (int end = 0; end < 2; end++) {
             const float d = end == 0 ? d0 : d1;
             if ((end == 1 && !capsule) || !(d < margin)) continue;
+            hits |= 32u << end;
             if (pass == 1 && base + n < L.maxcon) {
               RawContact rc;
 #pragma unroll
@@ -484,12 +503,14 @@ struct HEnv {
         // the maze boxes of the cells it can reach (wall, then platform), then the movable box geoms
         const float mg = r + fmaxf(gmarg, m->wall_margin);
         ext[0] += mg; ext[1] += mg;
-        int i0, i1, j0, j1;
-        cell_range(gp, ext, &i0, &i1, &j0, &j1);
+        int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
+        if (wanted >> 7) cell_range(gp, ext, &i0, &i1, &j0, &j1);
         const int nslot = m->elevated ? 2 : 1, nj = max(0, j1 - j0 + 1), ncell = nj * max(0, i1 - i0 + 1);
-        const int ncand = nslot * ncell + (BOX ? dv->nboxg : 0);
+        const int ncand = (wanted >> 7) ? nslot * ncell + (BOX ? dv->nboxg : 0) : 0;
 #pragma unroll 1
         for (int cand = 0; cand < ncand; cand++) {
+          const unsigned cbit = cand < 12 ? 128u << (2 * cand) : 0x80000000u;
+          if (!(wanted & (cand < 12 ? 3u * cbit : cbit))) continue;  // (pass 1) no environment of the warp hit this one
           float bc[3], bR[9], bh[3], margin, iw = invw;
           int other = -2, b2 = -1;
           if (cand < nslot * ncell) {
@@ -527,8 +548,8 @@ struct HEnv {
               n1 = 0;
             }
           }
-          if (n0) { if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r0, body, b2, iw, g, other); n++; }
-          if (n1) { if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r1, body, b2, iw, g, other); n++; }
+          if (n0) { hits |= cbit; if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r0, body, b2, iw, g, other); n++; }
+          if (n1) { hits |= cand < 12 ? cbit << 1 : cbit; if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r1, body, b2, iw, g, other); n++; }
         }
       }
     } else if (BOX) {
@@ -602,7 +623,7 @@ struct HEnv {
             if (base + k < L.maxcon) write_contact(L, base + k, rc[k], b1, b2, iw, g, other);
       }
     }
-    if (pass == 0) I(L.o_gcnt + item) = n;
+    if (pass == 0) I(L.o_gcnt + item) = min(n, 31) | (int)hits;
   }
 
   // ------------------------------------------------------------------ constraint rows (mj_makeConstraint)
@@ -766,6 +787,39 @@ struct HEnv {
       rhs -= f * rj;
 #pragma unroll
       for (int k = j + 1; k < NVP; k++) h[k] -= f * __shfl_sync(kAll, h[k], j, 16);
+    }
+    return rhs * invd;
+  }
+  // The same elimination for solver v2. `dg` is added to this lane's diagonal element on the fly (the joint-limit rows;
+  // 1 for the identity rows beyond the model), so the caller's row is a plain copy of the mass-matrix row. TOPO 1 =
+  // the Ant's tree (a free root, dofs 0-5, and 2-dof chains (6,7), (8,9), ... hanging off it): the pivots run from the
+  // leaves to the root, where elimination has no fill-in, and step j only touches the columns of the ancestors of j -
+  // 67 instead of 91 column updates (each a shuffle and a multiply-add) for the Ant.
+  template <int TOPO>
+  MMZ_DI float elim_solve2(float (&h)[NVP], float rhs, float dg) const {
+    float invd = 1.f;
+#pragma unroll
+    for (int jj = 0; jj < NVP; jj++) {
+      const int j = TOPO == 1 ? NVP - 1 - jj : jj;
+      const bool own = lane == j;
+      const float hj = own ? h[j] + dg : h[j];
+      const float piv = fmaxf(__shfl_sync(kAll, hj, j, 16), kMinVal);
+      float inv;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv));
+      const float rj = __shfl_sync(kAll, rhs, j, 16);
+      const float f = own ? 0.f : h[j] * inv;
+      invd = own ? inv : invd;
+      rhs -= f * rj;
+      if (TOPO == 1) {
+#pragma unroll
+        for (int k = 0; k < NVP; k++) {
+          const bool anc = j < 6 ? k < j : (k < 6 || ((j & 1) && k == j - 1));
+          if (anc) h[k] -= f * __shfl_sync(kAll, h[k], j, 16);
+        }
+      } else {
+#pragma unroll
+        for (int k = j + 1; k < NVP; k++) h[k] -= f * __shfl_sync(kAll, h[k], j, 16);
+      }
     }
     return rhs * invd;
   }
@@ -1094,10 +1148,7 @@ struct HEnv {
       if (__all_sync(kAll, done)) break;
       float hrow[NVP];
 #pragma unroll
-      for (int k = 0; k < NVP; k++) {
-        const float mk = mrow[k];
-        hrow[k] = (k == lane) ? (me ? mk + dadd : 1.f) : mk;
-      }
+      for (int k = 0; k < NVP; k++) hrow[k] = mrow[k];  // the diagonal terms of the limit rows join in the elimination
 #pragma unroll 1
       for (int c = 0; c < ncw; c++) {
         const float4 Wt = fg[2 * c + 1];
@@ -1112,7 +1163,8 @@ struct HEnv {
           hrow[k] += u0 * jk.x + u1 * jk.y + u2 * jk.z;
         }
       }
-      const float dr = elim_solve(hrow, me ? -grad : 0.f);
+      const float dg = me ? dadd : 1.f, rhs0 = me ? -grad : 0.f;
+      const float dr = L.topo == 1 ? elim_solve2<1>(hrow, rhs0, dg) : elim_solve2<0>(hrow, rhs0, dg);
       if (me && !done) W_(L.o_dir + lane) = dr;
       __syncwarp();
       float alpha = 1.f;
@@ -1222,6 +1274,9 @@ struct HEnv {
       if (__all_sync(kAll, done)) break;
     }
     __syncwarp();
+#ifdef MMZ_PHASE_TIMING
+    if (lane == 0) atomicAdd(&g_iter_hist[min(IW(L.o_cnt + TN_ITER), 15)], 1u);
+#endif
   }
 
   // RK4 bookkeeping of stage i for this warp's two environments (solver view, lane = dof), right after their solve:
@@ -1285,6 +1340,9 @@ struct HEnv {
 
   // ------------------------------------------------------------------ mj_forward
   MMZ_DI void forward(const TLayout& L, bool warmstart, int rk_stage = -1) {
+#ifdef MMZ_PHASE_TIMING
+    long long tick_ = clock64();
+#endif
     // A: the kinematic trees. Pass 0: the kinematic half of the roots. Pass 1: the subtree of every level-1 body is
     // walked by a PAIR of warps - one does the kinematic halves down the chain, its partner follows one body behind
     // with the dynamic halves (named barrier per pair) - while the roots' warps do the roots' dynamic halves and
@@ -1312,6 +1370,7 @@ struct HEnv {
           if (kind == A_ROOTDYN) named_arrive(15, dv->walk_root_count);
         }
         __syncthreads();
+        MMZ_TICK(pass);
       }
     }
     // B: geom poses, composite inertias, subtree forces
@@ -1325,6 +1384,7 @@ struct HEnv {
       }
     }
     __syncthreads();
+    MMZ_TICK(2);
     // C: contact counting, mass matrix rows, smooth forces
     const int nit = n_items(L);
     {
@@ -1336,16 +1396,18 @@ struct HEnv {
       }
     }
     __syncthreads();
+    MMZ_TICK(3);
     // D: contacts into their slots (over the slots of arrays that are dead by now, see the layout)
     for (int t = wid; t < nit; t += TW) collide_item(L, t, 1);
     if (wid == TW - 1) {
       int n = 0;
 #pragma unroll 1
-      for (int k = 0; k < nit; k++) n += I(L.o_gcnt + k);
+      for (int k = 0; k < nit; k++) n += I(L.o_gcnt + k) & 31;
       if (n > L.maxcon) I(L.o_cnt + TN_OVERFLOW) = 1;
       I(L.o_cnt + TN_CON) = min(n, L.maxcon);
     }
     __syncthreads();
+    MMZ_TICK(4);
     // E: contact rows
     {
       const int ncmax = __reduce_max_sync(kAll, I(L.o_cnt + TN_CON));
@@ -1354,13 +1416,23 @@ struct HEnv {
         else contact_rows(L, c);
       }
     }
-    __syncthreads();
+    // (solver v2 loads its registers first and has its own block barrier before it touches the Jacobian area: that one
+    // also orders the contact rows above against their readers)
+    if (!V2) __syncthreads();
+    MMZ_TICK(5);
     // solver view: warp w owns environments w and w + 16
     limit_rows_g(L);
     if (V2) solve_g2(L, warmstart);
     else solve_g(L, warmstart);
     if (rk_stage >= 0) rk_update_g(L, rk_stage);  // in the shadow of the wait for the slowest solve of the block
+#ifdef MMZ_PHASE_TIMING
+    const long long ts1_ = clock64();
     __syncthreads();
+    if (blockIdx.x == 0 && e == 0) { g_wsolve[wid] += ts1_ - tick_; g_wwait[wid] += clock64() - ts1_; }
+    MMZ_TICK(6);
+#else
+    __syncthreads();
+#endif
   }
 
   // ------------------------------------------------------------------ state checks

@@ -5,6 +5,7 @@
 // frame_skip x mj_step, _get_obs (maze_env.py:351-369), MazeTask.reward / termination (maze_task.py),
 // TimeLimit truncation (__init__.py:31) and the optional in-kernel auto-reset (reset_model, ant.py:84-96).
 #pragma once
+#include <cstdio>
 #include "mmz_hkernel.cuh"
 
 namespace mmz {
@@ -123,6 +124,16 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(h_smem_u32(smem)), "l"(A.model), "r"(L.model_bytes), "r"(h_smem_u32(&bar)) : "memory");
   }
+#ifdef MMZ_PHASE_TIMING
+  if (MODE == TMODE_STEP && tid == 0 && blockIdx.x == 0) {  // totals of the launches before this one
+    printf("phase cycles (block 0): rootkin %llu walk %llu B %llu C %llu D %llu E %llu solver %llu | iterations per solve:",
+           g_phase[0], g_phase[1], g_phase[2], g_phase[3], g_phase[4], g_phase[5], g_phase[6]);
+    for (int i = 0; i < 16; i++) printf(" %u", g_iter_hist[i]);
+    printf("\n  per warp solve / wait (kcycles):");
+    for (int i = 0; i < 16; i++) printf(" %llu/%llu", g_wsolve[i] / 1000, g_wwait[i] / 1000);
+    printf("\n");
+  }
+#endif
   HTask<NVP, BOX> T;
   T.m = reinterpret_cast<const mmz_model*>(smem);
   T.dv = reinterpret_cast<const TDerived*>(smem + ((sizeof(mmz_model) + 15) & ~15));
