@@ -9,7 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
+#include <utility>
+#include <vector>
 
 #include "../../include/mmz.h"
 #define MMZ_API_TU
@@ -292,6 +295,7 @@ bool configure_h(mmz_env* h, int* rc) {
   L.cstride = C_STRIDE;
   L.nstate = m.nq + 2 * m.nv + 3 * L.nlatch;
   const int nitems = L.ng + nbox * (1 + 2 * 9 + (nbox - 1));  // HEnv::n_items
+  if (nitems + 2 * m.nv > kMaxCTasks) return false;  // the phase C schedule of TDerived
   const int nvp = box ? 16 : 14;  // the solver reads qacc / dir up to the instance's padded nv (zero beyond nv)
   L.model_bytes = round_up(round_up((int)sizeof(mmz_model), 16) + (int)sizeof(TDerived), 16);
   int dev_smem = 0;
@@ -439,6 +443,37 @@ void make_tderived(const mmz_model& m, TDerived* d) {
   for (int g = 0; g < MMZ_MAXGEOM; g++) d->boxord[g] = -1;
   for (int g = 0; g < m.ngeom; g++)
     if (m.geom_type[g] == MMZ_GEOM_BOX) { d->boxord[g] = d->nboxg; d->boxg[d->nboxg++] = g; }
+  {
+    // Phase C schedule: tasks [0, nit) collision items, [nit, nit + nv) mass-matrix rows, then nv smooth forces;
+    // longest first onto the least loaded warp. Costs in units of ~250 cycles of one warp (measured on the Ant).
+    const int nit = m.ngeom + d->nboxg * (1 + 2 * 9 + (d->nboxg - 1)), nt = nit + 2 * m.nv;
+    std::vector<std::pair<int, int>> tasks;  // (cost, task)
+    for (int t = 0; t < nt; t++) {
+      int cost;
+      if (t < m.ngeom) cost = m.geom_type[t] == MMZ_GEOM_CAPSULE ? 10 : m.geom_type[t] == MMZ_GEOM_SPHERE ? 7 : 1;
+      else if (t < nit) cost = ((t - m.ngeom) % (1 + 2 * 9 + (d->nboxg - 1)) == 0) ? 6 : 14;  // plane-box : box-box
+      else if (t < nit + m.nv) { cost = 2; for (int j = t - nit; j >= 0; j = m.dof_parent[j]) cost++; }
+      else cost = 2;
+      tasks.push_back({cost, t});
+    }
+    std::stable_sort(tasks.begin(), tasks.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+    std::vector<int> load(TW, 0);
+    std::vector<std::vector<int>> mine(TW);
+    for (auto& ct : tasks) {
+      int w = 0;
+      for (int k = 1; k < TW; k++)
+        if (load[k] < load[w]) w = k;
+      load[w] += ct.first;
+      mine[w].push_back(ct.second);
+    }
+    int n = 0;
+    for (int w = 0; w < TW; w++) {
+      d->c_off[w] = n;
+      for (int t : mine[w])
+        if (n < kMaxCTasks) d->c_item[n++] = t;
+    }
+    d->c_off[TW] = n;
+  }
 }
 
 int configure(mmz_env* h, int G, int NVP) {

@@ -27,6 +27,7 @@ constexpr int TW = 16;  // warps per block
 constexpr int TE = 32;  // environments per block
 constexpr unsigned kAll = 0xffffffffu;
 constexpr int kTMaxNewton = 24;
+constexpr int kMaxCTasks = 160;  // collision items + 2 nv
 // roles of a warp in the tree walk (TDerived::walk_kind)
 enum { A_IDLE = 0, A_KIN = 1, A_PAIR_KIN = 2, A_PAIR_DYN = 3, A_ROOTDYN = 4, A_BOTH = 5 };
 constexpr int kTMaxLineSearch = 24;
@@ -60,6 +61,10 @@ struct TDerived {               // appended to the model blob in device memory
   int32_t sub_end[MMZ_MAXBODY];  // bodies are in depth-first order: the subtree of b is [b, sub_end[b])
   int32_t dof_act[MMZ_MAXDOF];   // actuators driving dof d: bit k set for actuator k
   int32_t dof_rel[MMZ_MAXDOF];   // bit k set: dof k is d, an ancestor or a descendant of d (the sparsity pattern of row d of M)
+  // phase C (contact counting, mass-matrix rows, smooth forces): the tasks of warp w, longest-processing-time-first
+  // over a cost model (a collision item is ~4 smooth-force tasks): c_item[c_off[w] .. c_off[w + 1])
+  int32_t c_off[TW + 1];
+  int32_t c_item[kMaxCTasks];
   int32_t pad2[3];
   float ident[9];
   float padf[3];
@@ -1388,8 +1393,9 @@ struct HEnv {
     // C: contact counting, mass matrix rows, smooth forces
     const int nit = n_items(L);
     {
-      const int nt = 2 * L.nv + nit;
-      for (int t = wid; t < nt; t += TW) {
+#pragma unroll 1
+      for (int i = dv->c_off[wid]; i < dv->c_off[wid + 1]; i++) {
+        const int t = dv->c_item[i];
         if (t < nit) collide_item(L, t, 0);
         else if (t < nit + L.nv) mass_row(L, t - nit);
         else smooth_dof(L, t - nit - L.nv);
