@@ -307,6 +307,7 @@ bool configure_h(mmz_env* h, int* rc) {
   L.o_ctrl = take(L.nu > 0 ? L.nu : 1); L.o_act = take(L.nu > 0 ? L.nu : 1);
   L.o_q0 = take(L.nq); L.o_v0 = take(L.nv); L.o_accv = take(L.nv); L.o_acca = take(L.nv);
   L.o_xpos = take(3 * L.nb);
+  L.o_lim = take(4 * L.nv);
   if (!box) {
     // Solver v2. In front: what stays live while the solver iterates. Then everything that is dead by then - the
     // solver view loads the mass matrix, the smooth forces and the motion axes into registers and passes a block

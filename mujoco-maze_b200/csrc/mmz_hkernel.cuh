@@ -80,6 +80,7 @@ struct TLayout {
   int o_iw, o_ic, o_vel, o_acc, o_frc, o_fsub;
   int o_M, o_smooth, o_dir;
   int o_con, o_cnt, o_gcnt, o_obs, o_act;
+  int o_lim;  // [nv][4] joint-limit rows of each dof: D lower, D upper, aref lower, aref upper (0 = no row)
   // solver v2 (models without box geoms): the stored contact Jacobian and the per-contact forces / Hessian weights, as
   // float4 arrays in natural [environment][contact] order. They OVERLAY the slots [o_nat, o_con) of the [slot][33]
   // workspace, whose arrays are all dead while the solver runs.
@@ -755,23 +756,33 @@ struct HEnv {
     for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(kAll, v, off);
     return v;
   }
-  // joint-limit rows of this lane's dof, in registers: side 0 = lower (J = +1), side 1 = upper (J = -1)
-  MMZ_DI void limit_rows_g(const TLayout& L) {
-    limD[0] = limD[1] = 0.f; limA[0] = limA[1] = 0.f;
-    const int jl = lane < L.nv ? m->dof_jnt[lane] : 0;
-    const bool limited = lane < L.nv && m->jnt_limited[jl] && m->jnt_type[jl] >= MMZ_JNT_SLIDE;
+  // Joint-limit rows of dof d, tree view (lane = environment): side 0 = lower (J = +1), side 1 = upper (J = -1). They
+  // depend on the state only, so idle warps compute them for all 32 environments at once while the roots' kinematics
+  // run; the solver view then just loads its lane's four numbers.
+  MMZ_DI void limit_rows_t(const TLayout& L, int d) {
+    const int jl = m->dof_jnt[d];
+    const bool limited = m->jnt_limited[jl] && m->jnt_type[jl] >= MMZ_JNT_SLIDE;
+    float D2[2] = {0.f, 0.f}, A2[2] = {0.f, 0.f};
+    if (limited) {
+      const float q = S(L.o_qpos + m->jnt_qadr[jl]), qv = S(L.o_qvel + d), margin = m->jnt_margin[jl];
 #pragma unroll
-    for (int s = 0; s < 2; s++) {  // unrolled: limD / limA must stay in registers (no dynamic indexing)
-      if (!limited) continue;
-      const float q = W_(L.o_qpos + m->jnt_qadr[jl]);
-      const float pos = s == 0 ? q - m->jnt_range[jl][0] : m->jnt_range[jl][1] - q, margin = m->jnt_margin[jl];
-      if (pos < margin) {
-        float D, kr, bb;
-        row_params(m->jnt_solref[jl], m->jnt_solimp[jl], pos, margin, m->dof_invweight0[lane], &D, &kr, &bb);
-        limD[s] = D;
-        limA[s] = -bb * (s == 0 ? 1.f : -1.f) * W_(L.o_qvel + lane) - kr;
+      for (int s = 0; s < 2; s++) {
+        const float pos = s == 0 ? q - m->jnt_range[jl][0] : m->jnt_range[jl][1] - q;
+        if (pos < margin) {
+          float D, kr, bb;
+          row_params(m->jnt_solref[jl], m->jnt_solimp[jl], pos, margin, m->dof_invweight0[d], &D, &kr, &bb);
+          D2[s] = D;
+          A2[s] = -bb * (s == 0 ? 1.f : -1.f) * qv - kr;
+        }
       }
     }
+    S(L.o_lim + 4 * d) = D2[0]; S(L.o_lim + 4 * d + 1) = D2[1]; S(L.o_lim + 4 * d + 2) = A2[0]; S(L.o_lim + 4 * d + 3) = A2[1];
+  }
+  // ... and the solver view (lane = dof) keeps them in registers
+  MMZ_DI void limit_rows_g(const TLayout& L) {
+    const bool me = lane < L.nv;
+    limD[0] = me ? W_(L.o_lim + 4 * lane) : 0.f; limD[1] = me ? W_(L.o_lim + 4 * lane + 1) : 0.f;
+    limA[0] = me ? W_(L.o_lim + 4 * lane + 2) : 0.f; limA[1] = me ? W_(L.o_lim + 4 * lane + 3) : 0.f;
   }
   // Lane i holds row i of the symmetric positive-definite H (NVP registers) and element i of the right-hand
   // side. Gauss-Jordan without pivoting: step j clears column j in EVERY other row (the rows above the pivot cost
@@ -1374,6 +1385,8 @@ struct HEnv {
           }
           if (kind == A_ROOTDYN) named_arrive(15, dv->walk_root_count);
         }
+        if (pass == 0)  // in the shadow of the roots' kinematics (the last warps first: the roots are on the first ones)
+          for (int d = TW - 1 - wid; d < L.nv; d += TW) limit_rows_t(L, d);
         __syncthreads();
         MMZ_TICK(pass);
       }
