@@ -1083,7 +1083,7 @@ struct Env {
           g = gsum<G>(g) + g0 + alpha * h0;
           h = gsum<G>(h) + h0;
           if (!lsdone) {
-            if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
+            if (fabsf(g) < MMZ_LS_TOL * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
             else {
               if (g < 0.f) lo = alpha; else hi = alpha;
               float next = alpha - g / h;
@@ -1098,6 +1098,7 @@ struct Env {
         // no row changed sides on [0, alpha] and alpha is the full Newton step: the new point is the solution of
         // this active set, the gradient pass that would confirm it is skipped (as in the hybrid kernel)
         exact = gballot(flipped) == 0 && lsconv && fabsf(alpha - 1.f) < 1e-3f;
+        if (exact) alpha = 1.f;  // the minimiser of that quadratic is the Newton step itself
       }
       bool moved = false;
       if (me && !done) {

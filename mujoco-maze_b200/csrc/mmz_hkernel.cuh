@@ -32,6 +32,7 @@ constexpr int kMaxCTasks = 160;  // collision items + 2 nv
 enum { A_IDLE = 0, A_KIN = 1, A_PAIR_KIN = 2, A_PAIR_DYN = 3, A_ROOTDYN = 4, A_BOTH = 5 };
 constexpr int kTMaxLineSearch = 24;
 
+
 enum { TMODE_STEP = 0, TMODE_FORWARD = 1, TMODE_OBSERVE = 2, TMODE_RESET = 3, TMODE_REFRESH = 4 };
 enum { T_DONE_BIT = 1, T_TRUNC_BIT = 2, T_UNSTABLE_BIT = 4 };
 enum { T_FLAG_AUTO_RESET = 1 };
@@ -1006,7 +1007,7 @@ struct HEnv {
           g = gsum16(g) + g0 + alpha * h0;
           h = gsum16(h) + h0;
           if (!lsdone) {
-            if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
+            if (fabsf(g) < MMZ_LS_TOL * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
             else {
               if (g < 0.f) lo = alpha; else hi = alpha;
               float next = alpha - g / h;
@@ -1022,6 +1023,7 @@ struct HEnv {
         // cost along the Newton direction of exactly that active set: the new point is the solution, and the
         // gradient pass that would confirm it is skipped.
         exact = gballot(flipped) == 0 && lsconv && fabsf(alpha - 1.f) < 1e-3f;
+        if (exact) alpha = 1.f;  // the minimiser of that quadratic is the Newton step itself
       }
       bool moved = false;
       if (me && !done) {
@@ -1246,7 +1248,7 @@ struct HEnv {
             g = gsum16(g) + g0 + alpha * h0;
             h = gsum16(h) + h0;
             if (!lsdone) {
-              if (fabsf(g) < 1e-6f * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
+              if (fabsf(g) < MMZ_LS_TOL * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
               else {
                 if (g < 0.f) lo = alpha; else hi = alpha;
                 float next = alpha - g / h;
@@ -1270,6 +1272,7 @@ struct HEnv {
         // of exactly that active set: the new point is the solution, and the gradient pass that would confirm it is
         // skipped.
         exact = !flipped && lsconv && fabsf(alpha - 1.f) < 1e-3f;
+        if (exact) alpha = 1.f;  // the minimiser of that quadratic is the Newton step itself
       }
       bool moved = false;
       if (me && !done) {
