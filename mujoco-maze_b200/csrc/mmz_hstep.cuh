@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
         T.task_rules(L, &outer, &term);
         reward = T.m->inner_reward_scale * inner + outer;
         if (term) bits |= T_DONE_BIT;
-        if (T.m->max_episode_steps > 0 && t >= T.m->max_episode_steps) bits |= T_DONE_BIT | T_TRUNC_BIT;
+        // gym's TimeLimit: info['TimeLimit.truncated'] = not done, i.e. only when the task itself did not end the episode
+        if (T.m->max_episode_steps > 0 && t >= T.m->max_episode_steps) bits |= T_DONE_BIT | (term ? 0 : T_TRUNC_BIT);
         info0 = S(L.o_qpos); info1 = S(L.o_qpos + 1);
         live = auto_reset && (bits & T_DONE_BIT);
         if (live) {  // the env that just ended starts its next episode inside this launch

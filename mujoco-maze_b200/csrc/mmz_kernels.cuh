@@ -227,6 +227,7 @@ struct Task : Env<G, NVP, FEAT> {
     bool reset_now = bad, noise = false, live = true;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
+      sync();  // every lane has read the ending episode's qpos (info, task rules) before the reset overwrites it (racecheck)
       if (live && reset_now) reset_state(L, seed, genv, *nreset_io, noise);
       sync();
       latch_objpos(L, live && !refresh);  // stale derived arrays are the reference's behaviour (quirk Q15)
@@ -241,11 +242,12 @@ struct Task : Env<G, NVP, FEAT> {
         task_rules(obs_s, &outer, &term);
         *reward = m->inner_reward_scale * inner + outer;
         if (term) bits |= DONE_BIT;
-        if (m->max_episode_steps > 0 && t >= m->max_episode_steps) bits |= DONE_BIT | TRUNC_BIT;
+        // gym's TimeLimit: info['TimeLimit.truncated'] = not done, i.e. only when the task itself did not end the episode
+        if (m->max_episode_steps > 0 && t >= m->max_episode_steps) bits |= DONE_BIT | (term ? 0 : TRUNC_BIT);
         info4[0] = qpos[0]; info4[1] = qpos[1]; info4[2] = fwd; info4[3] = -cc;
         live = auto_reset && (bits & DONE_BIT);
         if (!live && auto_reset && real) {  // no reset: the observation just assembled is the one to return
-          for (int i = lane; i < L.obs_dim; i += G) obs_g[i] = obs_s[i];
+          for (int i = lane; i < L.obs_core; i += G) obs_g[i == L.obs_core - 1 ? L.obs_dim - 1 : i] = obs_s[i];  // as write_obs
         }
         if (live) {  // the env that just ended starts its next episode inside this launch
           *nreset_io += 1;

@@ -187,8 +187,16 @@ def test_step_parity(env_id, torch_cuda, oracle_lib):
     _dump("step_" + env_id, stats)
     print({k: v for k, v in stats.items() if k != "worst"})
     assert (t1 == t0 + 1).all()
-    good = ev.max(1) <= 1e-3  # envs whose active set did not flip between fp32 and fp64
-    assert good.mean() >= 0.97, stats
+    # An fp32 / fp64 difference can flip the active set of a constraint row in a rare environment (velocity error
+    # > 1e-3). Measured on B200: none in any of the env ids (profiles/r2_parity.md, column "flips"). The bound is that
+    # count + 1, and the flipped environment still has to end the step where the oracle does: `done` is exact and the
+    # positions agree to 1e-2 for EVERY environment; the tight tolerances below hold for the rest.
+    good = ev.max(1) <= 1e-3
+    stats["flips"] = int((~good).sum())
+    _dump("step_" + env_id, stats)
+    assert (~good).sum() <= 1, stats
+    assert (done == rbits).all(), stats
+    assert eq.max() <= 1e-2, stats
     assert eq[good].max() <= 1e-4, stats
     assert (er[good] <= 1e-5 + 1e-4 * np.abs(rrew[good])).all(), stats
     assert (done[good] == rbits[good]).all(), stats
@@ -332,6 +340,75 @@ def test_reset_distribution_and_sharding(torch_cuda):
     assert torch.equal(torch.cat([o_a, o_b]), o_full), "sharded batches must be bit-identical to the single batch"
 
 
+@pytest.mark.parametrize("env_id,kind", [("PointUMaze-v0", "point"), ("PointPush-v0", "point"), ("SwimmerUMaze-v0", "swimmer")])
+def test_reset_distributions_point_and_swimmer(env_id, kind, torch_cuda):
+    """reset_model of the other agents: Point qpos0 + U(-0.1, 0.1), qvel U[0, 0.1) - the reference draws rand * 0.1, not a
+    symmetric range (point.py:72-75); Swimmer qpos0 + U(-0.1, 0.1), qvel U(-0.1, 0.1) (swimmer.py:56-65). Only the
+    agent's coordinates are perturbed; movable blocks start at rest in their cells."""
+    from mujoco_maze.backend import BatchedSim
+
+    model = make_model(env_id)
+    n = 16384
+    sim = BatchedSim(model, n)
+    sim.reset(seed=77)
+    q, v, t = (x.cpu().numpy() for x in sim.get_state())
+    naq, nav, nq = int(model.n_agent_q), int(model.n_agent_v), int(model.nq)
+    dq = q - np.asarray(model.qpos0, float)[None, :nq]
+    u_std = 0.2 / np.sqrt(12)
+    assert np.abs(dq[:, :naq]).max() <= 0.1 + 1e-6 and abs(dq[:, :naq].mean()) < 3e-3
+    assert abs(dq[:, :naq].std() - u_std) < 2e-3
+    if nq > naq:
+        assert np.abs(dq[:, naq:]).max() == 0 and np.abs(v[:, nav:]).max() == 0
+    va = v[:, :nav]
+    if kind == "point":
+        assert va.min() >= 0.0 and va.max() < 0.1 + 1e-7
+        assert abs(va.mean() - 0.05) < 2e-3 and abs(va.std() - 0.1 / np.sqrt(12)) < 2e-3
+    else:
+        assert np.abs(va).max() <= 0.1 + 1e-6 and abs(va.mean()) < 3e-3 and abs(va.std() - u_std) < 2e-3
+    # coordinates are independent draws: no two columns correlate
+    c = np.corrcoef(np.concatenate([dq[:, :naq], va], axis=1).T)
+    assert np.abs(c - np.eye(c.shape[0])).max() < 0.05
+    assert (t == 0).all()
+    sim.close()
+
+
+def test_true_distance_reward_R5(torch_cuda, oracle_lib):
+    """The reward the DistReward* names promise (-distance / scale, maze_task.py:93-99) is only reached when
+    DistRewardMixIn comes FIRST in the bases (in the registered classes GoalReward*.reward shadows
+    it). Such a task resolves to MMZ_REWARD_DIST in the kernel: checked against the Python method and the oracle."""
+    from mujoco_maze import maze_task as mt
+    from mujoco_maze.backend import BatchedSim
+    from mujoco_maze.model_compiler import compile_maze_model
+    from mujoco_maze.point import PointEnv
+
+    class TrueDistUMaze(mt.DistRewardMixIn, mt.GoalRewardUMaze):
+        pass
+
+    task = TrueDistUMaze(4.0)
+    assert mt.kernel_rule(task)[0] == mt.REWARD_DIST
+    model = compile_maze_model(PointEnv, task, 4.0)
+    assert int(model.reward_rule) == mt.REWARD_DIST
+    n = 96
+    rng = np.random.default_rng(12)
+    q, v = sample_states(model, "PointUMaze-v0", n, rng)
+    v = np.clip(v, -9, 9)
+    a = sample_actions(model, n, rng)
+    sim = BatchedSim(model, n)
+    sim.set_state(q, v, np.zeros(n, dtype=np.int32))
+    obs, rew, done, _ = sim.step(a)
+    obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+    want_py = np.array([task.reward(o.astype(np.float64)) for o in obs])
+    np.testing.assert_allclose(rew, want_py, rtol=1e-5, atol=1e-6)       # the reference's own formula on the same obs
+    assert (rew < 0).all() and rew.min() < -0.5
+    o = oracle_lib.OracleEnv(model)
+    o.L.ora_set_warmstart(o.h, 1)
+    for i in range(0, n, 3):
+        o.set_state(q[i], v[i], 0)
+        _, rr, bits, _ = o.step(a[i])
+        assert abs(rew[i] - rr) <= 1e-5 + 1e-4 * abs(rr) and int(done[i]) == int(bits)
+    sim.close()
+
+
 def test_truncation_and_auto_reset(torch_cuda):
     from mujoco_maze.backend import BatchedSim
 
@@ -355,6 +432,29 @@ def test_truncation_and_auto_reset(torch_cuda):
     t2 = t2.cpu().numpy()
     assert (t2[: n // 2] == 0).all() and (t2[n // 2:] == 12).all()
     assert np.abs(obs.cpu().numpy()[: n // 2, -1]).max() == 0  # fresh episode's observation
+
+
+def test_truncated_flag_is_not_set_when_the_task_ends_the_episode(torch_cuda):
+    """gym's TimeLimit sets info['TimeLimit.truncated'] = not done (reference __init__.py:31 wraps MazeEnv in it): an
+    episode the task terminates on its 1000th step is done, not truncated."""
+    from mujoco_maze.backend import BatchedSim
+
+    torch = torch_cuda
+    n = 64
+    model = make_model("PointUMaze-v1", num_envs=n)
+    sim = BatchedSim(model, n, auto_reset=False)
+    sim.reset(seed=3)
+    q, v, t = sim.get_state()
+    goal = torch.as_tensor(np.asarray(model.goal_pos, dtype=np.float32)[0, :2], device="cuda")
+    q[: n // 2, :2] = goal            # first half sits on the goal: the task terminates
+    v[:] = 0
+    t[:] = 999
+    sim.set_state(q, v, t)
+    _, _, done, _ = sim.step(torch.zeros((n, 2), device="cuda"))
+    d = done.cpu().numpy()
+    assert (d[: n // 2] == 1).all(), d[: n // 2]      # DONE only
+    assert (d[n // 2:] == 3).all(), d[n // 2:]        # DONE | TRUNCATED
+    sim.close()
 
 
 def test_reach_goal_reward_and_done(torch_cuda, oracle_lib):

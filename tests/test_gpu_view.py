@@ -87,3 +87,46 @@ def test_view_after_step_matches_oracle(key, torch_cuda, oracle_lib):
     assert np.quantile(err, 0.95) <= 2e-3 and float(np.abs(want[:, -76:-1]).max()) > 0.5
     np.testing.assert_allclose(obs[:, -1], 0.001, atol=1e-7)
     sim.close()
+
+
+@pytest.mark.parametrize("key", ["GoalRewardPush-point", "GoalRewardUMaze-ant"])
+def test_view_with_auto_reset_keeps_the_columns(key, torch_cuda, oracle_lib):
+    """A TOP_DOWN_VIEW task under the in-kernel auto-reset (VectorMazeEnv): the environments that do NOT reset must
+    get the state part, the view and t * 0.001 in the same columns as without auto-reset (the lanes-per-environment
+    kernel once copied obs_dim entries of an obs_core-sized buffer there)."""
+    from mujoco_maze.backend import BatchedSim
+    from mujoco_maze.model_compiler import compile_maze_model
+
+    case = G["cases"][CASES.index(key)]
+    model = compile_maze_model(_agent(case["agent"]), view_task(case["task"], case["scaling"]), case["scaling"])
+    rng = np.random.default_rng(6)
+    n, nq, nv, nu = 40, int(model.nq), int(model.nv), int(model.nu)
+    s = float(model.cell_size)
+    q = np.tile(np.asarray(model.qpos0, float)[:nq], (n, 1))
+    q[:, :2] += rng.uniform(-0.3 * s, 0.3 * s, size=(n, 2))
+    v = rng.normal(scale=0.3, size=(n, nv))
+    lo, hi = np.asarray(model.act_ctrlrange, float)[:nu].T
+    a = rng.uniform(lo, hi, size=(n, nu))
+    t0 = np.full(n, 41, dtype=np.int32)
+    t0[n // 2:] = 999  # the second half hits the TimeLimit in this step and restarts inside the launch
+    outs = []
+    for auto in (False, True):
+        sim = BatchedSim(model, n, auto_reset=auto)
+        sim.set_state(q, v, t0)
+        obs, rew, done, info = sim.step(a)
+        outs.append((obs.cpu().numpy().copy(), done.cpu().numpy().copy()))
+        sim.close()
+    (plain, d0), (auto, d1) = outs
+    h = n // 2
+    assert (d0[:h] & 1).sum() == 0 and ((d1[h:] & 1) == 1).all()
+    np.testing.assert_array_equal(auto[:h], plain[:h])                 # running episodes: identical, column for column
+    np.testing.assert_allclose(auto[:h, -1], 0.042, atol=1e-7)
+    np.testing.assert_allclose(auto[h:, -1], 0.0, atol=1e-7)           # fresh episodes start at t = 0 ...
+    assert float(np.abs(auto[h:, -76:-1]).max()) > 0.5                 # ... with a view of their reset position
+    o = oracle_lib.OracleEnv(model)
+    o.L.ora_set_warmstart(o.h, 1)
+    for i in range(0, h, 4):
+        o.set_state(q[i], v[i], int(t0[i]))
+        want = o.step(a[i])[0]
+        assert np.abs(auto[i, -76:-1] - want[-76:-1]).max() <= 5e-3
+        np.testing.assert_allclose(auto[i, :2], want[:2], atol=1e-3)
