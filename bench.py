@@ -15,9 +15,14 @@ collective (weak scaling). Prints ONE JSON line (rank 0).
   e2e       same metric through the C-ABI host call (mmz_step_host): pinned-host actions in,
             obs/reward/done/info out, copies inside the timed region
   roofline  algorithmic HBM bytes of one launch / its average duration vs the measured copy peak
-  cpu_baseline  the fp64 CPU restatement (oracle/, "port": mujoco-py is not installable here)
-            timed on this box's host cores on a bounded sample of the same workload (rank 0, N=1)
-  --impl reference  times that CPU restatement alone, all host threads, same config and metric
+            roofline.issue / roofline.fp32: the resources that actually bind (warp instructions and fp32 operations
+            per launch from the committed ncu capture, profiles/kernel_counters.json, over the LIVE launch time)
+  cpu_baseline  the reference's CPU implementation of the path on this box's host cores, bounded sample (rank 0,
+            N=1): the REAL reference loop (gym + mujoco-py / mujoco through baseline/_ref, kind "reference") when
+            tools/reference_loop.py --probe finds it importable, otherwise the fp64 CPU restatement (oracle/, kind
+            "port": never to be read as mujoco-py)
+  gather    (N > 1) a second timed loop with the observation all-gather of BASELINE configs[3]
+  --impl reference  times that CPU arm alone, all host threads, same config and metric
 """
 import argparse
 import json
@@ -45,7 +50,10 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="AntUMaze-v0:65536", help="ENV_ID:ENVS_PER_GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--gather-obs", action="store_true", help="all-gather the observations over NCCL inside the step")
+    ap.add_argument("--gather-obs", action="store_true", help="(N > 1) gather the observations inside the MAIN timed loop too")
+    ap.add_argument("--gather", default="peer", choices=["peer", "multicast", "nccl", "none"],
+                    help="(N > 1) how the second timed loop gathers the observations: peer / multicast = stores from the step "
+                         "kernel into every rank's gathered tensor (symmetric memory), nccl = all_gather_into_tensor after it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--ref-envs", type=int, default=0, help="--impl reference: environments per step (0 = auto)")
@@ -57,6 +65,34 @@ def host_cores():
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+def probe_reference():
+    """Is the reference's own loop (gym + MuJoCo + baseline/_ref) runnable on this box? (subprocess: same package name)"""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "reference_loop.py"), "--probe"],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"available": False, "why": f"probe failed: {type(e).__name__}: {e}"}
+
+
+def time_real_reference(env_id, steps, warmup, procs):
+    """gym.make(id); reset; step(action_space.sample()) - /root/reference/tests/test_envs.py:7-17 - one process per core."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "reference_loop.py"), "--time", env_id, "--steps", str(steps),
+                        "--warmup", str(warmup), "--procs", str(procs)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr[-500:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def workload_config(model, env_id, n_envs):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": f"{env_id}, {n_envs} parallel envs per GPU", "env_id": env_id, "envs_per_gpu": n_envs,
+            "frame_skip": int(model.frame_skip), "integrator": "RK4", "timestep": float(model.timestep),
+            "max_episode_steps": int(model.max_episode_steps), "auto_reset": True,
+            "actions": "uniform over ctrlrange, pre-generated (on device for the GPU arm)",
+            "episode_phase": "all environments reset (seed 0) right before the warm-up steps"}
 
 
 def make_model(env_id):
@@ -111,6 +147,15 @@ def time_cpu(model, n_envs, steps, warmup, threads, seed=0):
 
 def cpu_baseline(model, env_id, target_seconds):
     cores = host_cores()
+    p = probe_reference()
+    if p.get("available"):
+        r = time_real_reference(env_id, 100, 10, cores)  # the reference's own 100-step loop, one process per core
+        scale = max(1, int(target_seconds * r["env_steps_per_sec"] / cores / 100))
+        if scale > 1:
+            r = time_real_reference(env_id, 100 * min(scale, 50), 10, cores)
+        return {"value": r["env_steps_per_sec"], "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"{cores} processes x {r['steps']} steps of gym.make('{env_id}') after {r['warmup']} warm-up steps, "
+                          f"{p.get('mujoco')}, gym {p.get('gym')} (baseline/_ref)"}
     probe_envs = 8 * cores
     rate, _ = time_cpu(model, probe_envs, 2, 1, cores)
     steps = 10
@@ -120,7 +165,7 @@ def cpu_baseline(model, env_id, target_seconds):
     return {
         "value": value, "unit": UNIT, "cores": cores, "kind": "port",
         "sample": f"{n_envs} {env_id} envs x {steps} steps after 2 warm-up steps ({dt:.1f} s), fp64 CPU restatement "
-                  f"(oracle/mmz_oracle.c, OpenMP); mujoco-py / MuJoCo are not installable in this image",
+                  f"(oracle/mmz_oracle.c, OpenMP) - NOT mujoco-py: {p.get('why', 'reference not importable')}",
     }
 
 
@@ -180,30 +225,47 @@ def algorithmic_bytes_per_env_step(model, with_info=True):
     return b + (16 if with_info else 0)
 
 
+def survey_bytes_per_env_step(model):
+    """B = 4 (2 (nq + nv) + nu + obs_dim + 3) + 1 (no persisted warm start, counters or info)."""
+    return 4 * (2 * (int(model.nq) + int(model.nv)) + int(model.nu) + int(model.obs_dim) + 3) + 1
+
+
 def run_reference(args, env_id, n_envs):
-    """The reference arm: the CPU implementation of the path on the host cores (rank 0 only)."""
+    """The reference arm: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     model = make_model(env_id)
     cores = host_cores()
-    if args.ref_envs:
-        sample = args.ref_envs
+    p = probe_reference()
+    if p.get("available"):
+        r = time_real_reference(env_id, max(100, args.steps), max(10, args.warmup), cores)
+        value, dt, steps_timed = r["env_steps_per_sec"], r["steps"] / (r["env_steps_per_sec"] / cores), r["steps"]
+        kind, dtype = "reference", "f64"
+        sample = (f"{cores} processes x {r['steps']} steps of gym.make('{env_id}') (the reference's own loop, "
+                  f"{p.get('mujoco')}, gym {p.get('gym')}, baseline/_ref)")
+        ms = 1e3 * dt / steps_timed
+        note = "reference arm = the unmodified reference through gym.make, one process per host core"
     else:
-        rate, _ = time_cpu(model, 8 * cores, 2, 1, cores)
-        budget = 150.0  # seconds for the whole run
-        sample = int(rate * budget / max(1, args.steps + args.warmup))
-        sample = max(cores, min(n_envs, sample) // cores * cores)
-    value, dt = time_cpu(model, sample, args.steps, args.warmup, cores)
+        if args.ref_envs:
+            sample_envs = args.ref_envs
+        else:
+            rate, _ = time_cpu(model, 8 * cores, 2, 1, cores)
+            budget = 150.0  # seconds for the whole run
+            sample_envs = int(rate * budget / max(1, args.steps + args.warmup))
+            sample_envs = max(cores, min(n_envs, sample_envs) // cores * cores)
+        value, dt = time_cpu(model, sample_envs, args.steps, args.warmup, cores)
+        kind, dtype = "port", "f64"
+        sample = f"{sample_envs} envs per step x {args.steps} steps, fp64 CPU restatement (oracle/), OpenMP {cores} threads"
+        ms = 1e3 * dt / args.steps
+        note = ("reference arm = fp64 CPU restatement of MazeEnv.step (oracle/), NOT mujoco-py: " + p.get("why", ""))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{env_id}, {n_envs} parallel envs per GPU", "sample_envs_per_step": sample,
-                   "note": "reference arm = fp64 CPU restatement of MazeEnv.step (oracle/); the reference's own "
-                           "mujoco-py loop cannot be installed here (closed MuJoCo 2.0 binary, no network)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} envs per step x {args.steps} steps, OpenMP {cores} threads"},
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": workload_config(model, env_id, n_envs),
+        "details": {"note": note, "probe": p},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -241,19 +303,51 @@ def main():
     rew = torch.empty((n_envs,), device=dev)
     done = torch.empty((n_envs,), device=dev, dtype=torch.uint8)
     info = torch.empty((n_envs, 4), device=dev)
-    gathered = torch.empty((world * n_envs, od), device=dev) if (args.gather_obs and world > 1) else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    gather_state = {"mode": "none", "nccl_out": None, "peer": None}
+
+    def set_gather(mode):
+        """none | nccl (all_gather_into_tensor after the kernel) | peer / multicast (stores from the step kernel)"""
+        if gather_state["peer"] is not None and mode not in ("peer", "multicast"):
+            gather_state["peer"].close()
+        if mode == "nccl" and gather_state["nccl_out"] is None:
+            gather_state["nccl_out"] = torch.empty((world * n_envs, od), device=dev)
+        if mode in ("peer", "multicast") and gather_state["peer"] is None:
+            from mujoco_maze.sharding import PeerObsGatherer
+
+            gather_state["peer"] = PeerObsGatherer(sim, world * n_envs, rank * n_envs, multicast=(mode == "multicast"))
+        elif mode in ("peer", "multicast"):
+            sim.set_obs_peers(gather_state["peer"]._ptrs, rank * n_envs, gather_state["peer"].multicast)
+        gather_state["mode"] = mode
 
     def one_step(i):
         sim.step_into(acts[i % len(acts)], obs, rew, done, info)
-        if gathered is not None:
-            dist.all_gather_into_tensor(gathered, obs)
+        if gather_state["mode"] == "nccl":
+            dist.all_gather_into_tensor(gather_state["nccl_out"], obs)
+        elif gather_state["mode"] in ("peer", "multicast"):
+            gather_state["peer"].sync()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_loop(first, steps):
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for i in range(steps):
+            flush.zero_()
+            starts[i].record()
+            one_step(first + i)
+            ends[i].record()
+        barrier()
+        total = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, ends))], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        return float(total.item())
+
+    if args.gather_obs and world > 1:
+        set_gather(args.gather)
     sim.reset(seed=0)
     for i in range(args.warmup):
         one_step(i)
@@ -263,24 +357,38 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = sim.launch_count
-    done_frac = 0.0
-    for i in range(args.steps):
-        flush.zero_()
-        starts[i].record()
-        one_step(args.warmup + i)
-        ends[i].record()
-    barrier()
+    total_ms = timed_loop(args.warmup, args.steps)
     launches = sim.launch_count - launches0
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
     done_frac = float((done & 1).float().mean().item())
     unstable = int(((done & 4) != 0).sum().item())
+
+    # ---- BASELINE configs[3]: the same loop with the observations of all ranks gathered into one tensor per rank
+    gather = None
+    if world > 1 and args.gather != "none" and not args.gather_obs:
+        mode, why = args.gather, None
+        try:
+            set_gather(mode)
+        except Exception as e:  # noqa: BLE001  (no symmetric memory on this box: fall back to the NCCL collective)
+            why, mode = f"{type(e).__name__}: {e}"[:200], "nccl"
+            set_gather(mode)
+        for i in range(3):
+            one_step(i)
+        barrier()
+        gsteps = max(5, args.steps)
+        g_ms = timed_loop(args.warmup + args.steps, gsteps)
+        check = None
+        if mode != "nccl":  # the fused gather must equal the collective bit for bit
+            ref = torch.empty((world * n_envs, od), device=dev)
+            dist.all_gather_into_tensor(ref, obs)
+            check = bool(torch.equal(ref, gather_state["peer"].out))
+        gather = {"ms_per_step": g_ms / gsteps, "ms_per_step_no_gather": total_ms / args.steps, "bytes_per_rank": n_envs * od * 4,
+                  "method": {"peer": "stores from the step kernel into every rank's gathered tensor (symmetric memory, P2P)",
+                             "multicast": "multimem.st from the step kernel through one NVLS multicast address",
+                             "nccl": "dist.all_gather_into_tensor after the step kernel"}[mode],
+                  "steps": gsteps, "equals_nccl_all_gather": check, "fallback_reason": why}
+        set_gather("none")
+        sim.set_obs_peers([], 0)
 
     # ---- end to end through the C-ABI host call: pinned host buffers, copies inside the timed region
     h_acts = [a.cpu().pin_memory() for a in acts[:4]]
@@ -305,27 +413,44 @@ def main():
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        sm_max_mhz = 1965.0
         if os.path.exists(peaks_path):
             with open(peaks_path) as f:
-                peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+                pk = json.load(f)
+            peak, peak_src = float(pk["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+            sm_max_mhz = float(pk.get("sm_max_mhz", sm_max_mhz))
         else:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
         ms_per_step = total_ms / args.steps
-        bytes_per_launch = algorithmic_bytes_per_env_step(model) * n_envs
-        achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")  # written from an ncu --set full capture
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get(args.workload)
+        t_launch = ms_per_step * 1e-3
+        b_full, b_survey = algorithmic_bytes_per_env_step(model), survey_bytes_per_env_step(model)
+        achieved = b_full * n_envs / t_launch / 1e9
+        # counters of ONE launch of this workload from the committed ncu capture (tools/ncu_counters.py); the live launch
+        # time above turns them into the utilisation of the resources that actually bind the step
+        counters, issue, fp32, traffic = None, None, None, None
+        cpath = os.path.join(ROOT, "profiles", "kernel_counters.json")
+        if os.path.exists(cpath):
+            with open(cpath) as f:
+                counters = json.load(f).get(args.workload)
+        clk_hz = 1e6 * float((clocks or {}).get("sm_mhz") or sm_max_mhz)
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        if counters:
+            traffic = counters["dram_bytes"]
+            issue = {"warp_inst_per_launch": counters["warp_inst"], "frac": counters["warp_inst"] / (t_launch * n_sm * 4 * clk_hz),
+                     "peak": "4 warp instructions / cycle / SM at the SM clock sampled during the timed region",
+                     "stall_share_pct": counters.get("stall_share_pct"), "source": "profiles/kernel_counters.json <- " + counters["source"]}
+            fp32 = {"flop_per_launch": counters["fp32_flop"], "achieved_tflops": counters["fp32_flop"] / t_launch / 1e12,
+                    "peak_tflops": n_sm * 128 * 2 * clk_hz / 1e12,
+                    "frac": counters["fp32_flop"] / t_launch / (n_sm * 128 * 2 * clk_hz),
+                    "flop_per_env_step": counters["fp32_flop"] / n_envs}
         line = {
             "metric": METRIC, "value": world * n_envs * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{env_id}, {n_envs} parallel envs per GPU", "frame_skip": int(model.frame_skip),
-                       "integrator": "RK4", "auto_reset": True, "l2": "flushed (256 MiB write) between timed steps",
-                       "actions": "pre-generated on device, uniform over ctrlrange", "gather_obs": gathered is not None,
-                       "kernel": sim.kernel_config, "done_frac_last_step": done_frac, "unstable_last_step": unstable},
+            "config": workload_config(model, env_id, n_envs),
+            "details": {"l2": "flushed (256 MiB write) between timed steps", "gather_obs_in_main_loop": gather_state["mode"] != "none" and bool(args.gather_obs),
+                        "kernel": sim.kernel_config, "done_frac_last_step": done_frac, "unstable_last_step": unstable,
+                        "line_search_tolerance": 1e-3},
             "clocks": clocks,
             "e2e": {"value": world * n_envs * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": n_envs * nu * 4, "d2h_bytes_per_step": n_envs * (od * 4 + 4 + 1 + 16),
@@ -333,11 +458,19 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "bytes_per_env_step": algorithmic_bytes_per_env_step(model),
+                         "traffic_note": "dram__bytes_read + write of one launch under ncu's default cache control (caches "
+                                         "flushed before every replay, i.e. cold like this bench's flushed L2): the reads are "
+                                         "the state tile + actions; the outputs stay in the 126 MB L2 past the end of the launch",
+                         "bytes_per_env_step": b_full, "bytes_per_env_step_survey": b_survey,
+                         "achieved_survey_bytes": b_survey * n_envs / t_launch / 1e9,
                          "kernel": sim.kernel_config.get("kernel", "maze_kernel"),
-                         "note": "nominal bound; the step is fp32-issue / latency bound (about 1 MFLOP per Ant env-step "
-                                 "against 0.5 KB of HBM traffic), see DESIGN.md"},
+                         "issue": issue, "fp32": fp32,
+                         "note": "HBM is the nominal bound of a one-pass state update and is 3 orders of magnitude away; "
+                                 "what binds is the issue rate between block barriers and the waits at them (issue, fp32, "
+                                 "stall_share_pct; DESIGN.md section 5)"},
         }
+        if gather is not None:
+            line["gather"] = gather
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(model, env_id, args.cpu_seconds)
         print(json.dumps(line), flush=True)

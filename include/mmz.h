@@ -83,6 +83,17 @@ const char* mmz_kernel_name(mmz_handle h);
  * reference counterpart: the reference holds one mjData per Python object (maze_env.py:218). */
 int mmz_set_env_offset(mmz_handle h, int first_global_env);
 
+/* Fused observation gather - BASELINE configs[3], "NCCL over NVLink used only to all-gather observations when the
+ * caller wants a single tensor": every following mmz_step ALSO stores the observation row of environment e at row
+ * `row_offset + e` of each of the `npeers` buffers d_peer_obs[k] (row-major [total_envs][obs_dim] float32: this rank's
+ * gathered tensor and the peer-mapped gathered tensors of the other ranks, e.g. CUDA IPC / symmetric memory), from
+ * inside the step kernel, so no collective runs after it. With `multicast` non-zero d_peer_obs[0] is ONE multicast
+ * (NVLS) address that fans out to every rank (multimem.st). npeers = 0 turns the gather off. The caller orders the
+ * ranks (a barrier after the step, before anyone reads the gathered tensors or starts the next step). No reference
+ * counterpart: the reference holds one mjData per Python object (maze_env.py:218). Not available for tasks with
+ * TOP_DOWN_VIEW (MMZ_ERR_INVALID). */
+int mmz_set_obs_peers(mmz_handle h, float* const* d_peer_obs, int npeers, int64_t row_offset, int multicast);
+
 /* MazeEnv.reset (maze_env.py:371-382) + reset_model (point.py:71-81,
  * ant.py:84-96, swimmer.py:55-68) for the envs whose d_mask byte is non-zero
  * (NULL = all). Noise is Philox4x32-10 keyed by (seed, env index): the

@@ -91,6 +91,7 @@ struct mmz_env {
   char kname[48] = "";
   float tol = 2e-6f;  // Newton convergence tolerance of the hybrid kernel (fp32 round-off floor)
   TLayout TL;
+  ObsPeers peers = {};  // fused observation gather (mmz_set_obs_peers)
   mmz::hkernel_fn tfn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -220,6 +221,7 @@ int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s, int block0 = 0, int n
     T.qacc_out = A.qacc_out; T.diag = A.diag; T.mask = A.mask; T.seed = A.seed;
     T.flags = h->flags; T.env_offset = h->env_offset; T.tol = h->tol;
     T.block0 = block0;
+    if (mode == MODE_STEP) T.peers = h->peers;
     h->tfn[mode]<<<nblocks > 0 ? nblocks : h->npad / TE, TW * 32, h->smem_bytes, s>>>(T);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -236,6 +238,7 @@ int launch(mmz_env* h, int mode, KArgs& A, cudaStream_t s, int block0 = 0, int n
   int epb = h->tpb / h->G;
   int blocks = nblocks > 0 ? nblocks : (h->npad + epb - 1) / epb;  // padding environments run too (warp-uniform control flow)
   A.block0 = block0;
+  if (mode == MODE_STEP) A.peers = h->peers; else memset(&A.peers, 0, sizeof A.peers);
   h->fn[mode]<<<blocks, h->tpb, h->smem_bytes, s>>>(A);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -537,7 +540,7 @@ int configure(mmz_env* h, int G, int NVP) {
 
 extern "C" {
 
-int mmz_abi_version(void) { return 5; }
+int mmz_abi_version(void) { return 6; }
 const char* mmz_last_error(void) { return g_err; }
 
 int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, uint32_t flags, mmz_handle* out) {
@@ -655,6 +658,21 @@ const char* mmz_kernel_name(mmz_handle h) {
 int mmz_set_step_diag(mmz_handle h, int32_t* d_diag) {
   if (!h) return fail(MMZ_ERR_INVALID, "null handle");
   h->d_step_diag = d_diag;
+  return MMZ_OK;
+}
+
+int mmz_set_obs_peers(mmz_handle h, float* const* d_peer_obs, int npeers, int64_t row_offset, int multicast) {
+  if (!h) return fail(MMZ_ERR_INVALID, "null handle");
+  if (npeers < 0 || npeers > MMZ_MAXPEERS || (npeers > 0 && !d_peer_obs) || row_offset < 0 || (multicast && npeers != 1))
+    return fail(MMZ_ERR_INVALID, "mmz_set_obs_peers: 0..%d buffers (exactly one for a multicast address), row_offset >= 0", MMZ_MAXPEERS);
+  if (npeers > 0 && h->hm.view_dim)
+    return fail(MMZ_ERR_INVALID, "mmz_set_obs_peers: tasks with TOP_DOWN_VIEW fill part of the observation in a second kernel and cannot be gathered in the step kernel");
+  memset(&h->peers, 0, sizeof h->peers);
+  for (int k = 0; k < npeers; k++) {
+    if (!d_peer_obs[k]) return fail(MMZ_ERR_INVALID, "mmz_set_obs_peers: buffer %d is null", k);
+    h->peers.buf[k] = d_peer_obs[k];
+  }
+  h->peers.n = npeers; h->peers.row0 = row_offset; h->peers.multicast = multicast ? 1 : 0;
   return MMZ_OK;
 }
 

@@ -108,6 +108,7 @@ struct TArgs {
   int block0;          // first block of this launch (mmz_step_host pipelines block ranges)
   int env_offset;
   float tol;           // Newton convergence: |grad_d| <= tol * (magnitude of the terms grad_d is the sum of)
+  ObsPeers peers;      // TMODE_STEP: fused observation gather (mmz_layout.h)
 };
 
 

@@ -242,7 +242,10 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
       const int nreal = min(TE, A.n - env0);
       for (int idx = tid; idx < nreal * L.obs_core; idx += TW * 32) {
         const int ee = idx / L.obs_core, i = idx - ee * L.obs_core;
-        A.obs[(size_t)(env0 + ee) * L.obs_dim + obs_column(L, i)] = ws[(L.o_obs + i) * HS + ee];
+        const float v = ws[(L.o_obs + i) * HS + ee];
+        A.obs[(size_t)(env0 + ee) * L.obs_dim + obs_column(L, i)] = v;
+        // fused observation gather: the same contiguous chunk again, into every rank's gathered tensor over NVLink
+        if (A.peers.n) peer_store(A.peers, (size_t)(A.peers.row0 + env0 + ee) * L.obs_dim + obs_column(L, i), v);
       }
     }
     if (wid == 0) {

@@ -40,6 +40,7 @@ struct KArgs {
   unsigned flags;
   int env_offset;       // global index of env 0 (keeps the Philox streams independent of the sharding)
   int block0;           // first block of this launch: mmz_step_host runs the batch as a few pipelined block ranges
+  ObsPeers peers;       // MODE_STEP: fused observation gather (mmz_layout.h)
 };
 
 MMZ_DI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -355,6 +356,11 @@ maze_kernel(const __grid_constant__ KArgs A) {
       }
       if (real && A.info && T.lane < 4) A.info[(size_t)env * 4 + T.lane] = info4[T.lane];
       if (real && A.diag && T.lane < 4) A.diag[(size_t)env * 4 + T.lane] = T.cnt(L)[N_ITER_SUM + T.lane];
+      if (A.peers.n && real) {  // fused observation gather: obs_s holds the row that went to A.obs (write_obs)
+        T.sync();
+        for (int i = T.lane; i < L.obs_core; i += G)
+          peer_store(A.peers, (size_t)(A.peers.row0 + env) * L.obs_dim + (i == L.obs_core - 1 ? L.obs_dim - 1 : i), obs_s[i]);
+      }
     } else if (MODE == MODE_FORWARD) {
       for (int a = T.lane; a < L.nu; a += G)
         T.w[L.o_ctrl + a] = (T.m->step_kind == MMZ_STEP_TELEPORT || !real) ? 0.f : A.action[(size_t)env * L.nu + a];

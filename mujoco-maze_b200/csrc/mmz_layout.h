@@ -45,6 +45,28 @@ enum { N_CON = 0, N_LIM = 1, N_ITER = 2, N_OVERFLOW = 3,
        N_ITER_SUM = 4, N_LS_SUM = 5, N_CON_MAX = 6, N_CAPPED = 7, N_CNT = 8 };  // 4..7: accumulated over one env-step
 
 constexpr int MMZ_MAXPAIR = 32;
+constexpr int MMZ_MAXPEERS = 8;
+
+// Fused observation gather (mmz_set_obs_peers): the step kernels store every observation row they write a second time
+// at row `row0 + env` of each peer buffer - [total_envs][obs_dim] float32 in the other ranks' (peer-mapped) and this
+// rank's memory - or ONCE through an NVLS multicast address that fans out to all of them (`multicast`). The NVLink
+// transfers overlap the physics of the blocks that are still running: no collective runs after the kernel.
+struct ObsPeers {
+  float* buf[MMZ_MAXPEERS];
+  long long row0;
+  int n;          // 0 = off
+  int multicast;  // buf[0] is a multicast address: multimem.st
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void peer_store(const ObsPeers& P, size_t idx, float v) {
+  if (P.multicast) {
+    asm volatile("multimem.st.global.f32 [%0], %1;" ::"l"(P.buf[0] + idx), "f"(v) : "memory");
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < P.n; k++) P.buf[k][idx] = v;
+  }
+}
+#endif
 
 struct Derived {            // appended to the model blob in device memory
   int32_t anc[MMZ_MAXBODY];  // bit a set in anc[b]: body a is b or an ancestor of b

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_PKG_ROOT, os.environ.get("MMZ_LIB", "libmmz.so"))
 MMZ_DONE, MMZ_TRUNCATED, MMZ_UNSTABLE = 1, 2, 4
 MMZ_AUTO_RESET = 1
 LAYOUT_ENV_MAJOR, LAYOUT_SOA = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _lib = None
 
@@ -49,6 +49,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "mmz_kernel_config": ([vp, ip, ip, ip, ip, ip], i32),
         "mmz_kernel_name": ([vp], ctypes.c_char_p),
         "mmz_set_env_offset": ([vp, i32], i32),
+        "mmz_set_obs_peers": ([vp, ctypes.POINTER(vp), i32, ctypes.c_int64, i32], i32),
         "mmz_set_step_diag": ([vp, vp], i32),
         "mmz_reset": ([vp, vp, u64, vp, vp], i32),
         "mmz_step": ([vp, vp, vp, vp, vp, vp, vp], i32),
@@ -74,7 +75,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = (
-    "mmz_create", "mmz_dims", "mmz_kernel_config", "mmz_kernel_name", "mmz_set_env_offset", "mmz_set_step_diag", "mmz_reset", "mmz_step", "mmz_step_host", "mmz_observe", "mmz_get_state",
+    "mmz_create", "mmz_dims", "mmz_kernel_config", "mmz_kernel_name", "mmz_set_env_offset", "mmz_set_obs_peers", "mmz_set_step_diag", "mmz_reset", "mmz_step", "mmz_step_host", "mmz_observe", "mmz_get_state",
     "mmz_set_state", "mmz_forward", "mmz_render", "mmz_launch_count", "mmz_last_error", "mmz_destroy", "mmz_abi_version",
 )
 
@@ -197,6 +198,13 @@ class BatchedSim:
         self._check(self.lib.mmz_render(self._h, int(first_env), count, int(width), int(height), rgb.data_ptr(),
                                         self._stream()))
         return rgb
+
+    def set_obs_peers(self, ptrs, row_offset: int, multicast: bool = False):
+        """Fused observation gather (include/mmz.h: mmz_set_obs_peers): device addresses of the [total, obs_dim] float32
+        gathered tensors of every rank (or one multicast address); `ptrs` empty turns it off."""
+        ptrs = [int(p) for p in ptrs]
+        arr = (ctypes.c_void_p * max(1, len(ptrs)))(*ptrs)
+        self._check(self.lib.mmz_set_obs_peers(self._h, arr, len(ptrs), int(row_offset), int(bool(multicast))))
 
     def enable_step_diag(self, on: bool = True):
         """Per-env solver diagnostics of every following step: [N, 4] int32 (see include/mmz.h)."""

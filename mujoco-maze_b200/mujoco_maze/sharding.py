@@ -5,8 +5,9 @@ reference maze_env.py:218), so a batch of `total` environments is split into con
 env-index ranges, one per rank. The reset noise is keyed by the GLOBAL env index
 (`env_offset`, include/mmz.h: mmz_set_env_offset), which makes 1 GPU x N and G GPUs x N/G
 produce the same trajectories. The only collective is optional: all-gathering the observations
-when the caller wants one tensor (NCCL on GPUs; the same code runs over gloo on CPU tensors,
-which is how tests/test_sharding_gloo.py covers it).
+when the caller wants one tensor. Two ways: `ObsGatherer` (NCCL on GPUs; the same code runs over gloo on CPU
+tensors, which is how tests/test_sharding_gloo.py covers it) and `PeerObsGatherer`, where the step kernel itself
+stores the observations into every rank's gathered tensor over NVLink (symmetric memory; no collective at all).
 """
 
 from typing import Optional, Tuple
@@ -77,3 +78,46 @@ class ObsGatherer:
             for r, (s, c) in enumerate(self.bounds):
                 self.out[s:s + c].copy_(self.blocks[r * self.maxc:r * self.maxc + c])
         return self.out
+
+
+class PeerObsGatherer:
+    """Fused gather: `mmz_step` stores each observation row a second time into the `[total, obs_dim]` tensor of EVERY rank
+    (peer-mapped symmetric memory, or one NVLS multicast address), from inside the step kernel - the NVLink transfers
+    overlap the physics of the blocks still running, and nothing runs after the kernel but `sync()`, a device-side
+    barrier on the current stream (signal pads of the same symmetric allocation).
+
+        g = PeerObsGatherer(sim, total_envs, first_env)      # collective: every rank of the group calls it
+        sim.step(actions); g.sync(); policy(g.out)          # g.out == ObsGatherer's result, bit for bit
+    """
+
+    def __init__(self, sim, total_envs: int, first_env: int, group=None, multicast: bool = False):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.sim, self.torch = sim, torch
+        group = group or dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("the fused gather holds at most 8 peer addresses (one NVSwitch node)")
+        with torch.cuda.device(sim.device):
+            self.out = symm_mem.empty((int(total_envs), sim.obs_dim), dtype=torch.float32, device=sim.device)
+            self.out.zero_()
+            self.hdl = symm_mem.rendezvous(self.out, group)
+        self.multicast = bool(multicast and self.hdl.has_multicast_support and self.hdl.multicast_ptr)
+        if self.multicast:
+            ptrs = [self.hdl.multicast_ptr + (self.out.data_ptr() - self.hdl.buffer_ptrs[self.hdl.rank])]
+        else:  # one view of every rank's buffer (this rank's own included), same offset inside the allocation
+            self._views = [self.hdl.get_buffer(r, tuple(self.out.shape), torch.float32) for r in range(self.world)]
+            ptrs = [v.data_ptr() for v in self._views]
+        self._ptrs = ptrs
+        sim.set_obs_peers(ptrs, int(first_env), self.multicast)
+        self.sync()
+
+    def sync(self):
+        """All ranks' stores of the step just launched are complete and visible after this (stream-ordered)."""
+        self.hdl.barrier(channel=0)
+        return self.out
+
+    def close(self):
+        self.sim.set_obs_peers([], 0)
