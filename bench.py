@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--workload", default="AntUMaze-v0:65536", help="ENV_ID:ENVS_PER_GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gather-obs", action="store_true", help="(N > 1) gather the observations inside the MAIN timed loop too")
-    ap.add_argument("--gather", default="peer", choices=["peer", "multicast", "nccl", "none"],
+    ap.add_argument("--gather", default="multicast", choices=["peer", "multicast", "nccl", "none"],
                     help="(N > 1) how the second timed loop gathers the observations: peer / multicast = stores from the step "
                          "kernel into every rank's gathered tensor (symmetric memory), nccl = all_gather_into_tensor after it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -372,16 +372,19 @@ def main():
         except Exception as e:  # noqa: BLE001  (no symmetric memory on this box: fall back to the NCCL collective)
             why, mode = f"{type(e).__name__}: {e}"[:200], "nccl"
             set_gather(mode)
-        for i in range(3):
+        sim.reset(seed=0)  # the same episode phase (and, the physics being deterministic, the same work) as the loop above
+        for i in range(args.warmup):
             one_step(i)
         barrier()
-        gsteps = max(5, args.steps)
-        g_ms = timed_loop(args.warmup + args.steps, gsteps)
+        gsteps = args.steps
+        g_ms = timed_loop(args.warmup, gsteps)
         check = None
         if mode != "nccl":  # the fused gather must equal the collective bit for bit
             ref = torch.empty((world * n_envs, od), device=dev)
             dist.all_gather_into_tensor(ref, obs)
             check = bool(torch.equal(ref, gather_state["peer"].out))
+        if mode == "multicast" and not gather_state["peer"].multicast:
+            mode = "peer"  # no NVLS multicast on this box: per-peer stores
         gather = {"ms_per_step": g_ms / gsteps, "ms_per_step_no_gather": total_ms / args.steps, "bytes_per_rank": n_envs * od * 4,
                   "method": {"peer": "stores from the step kernel into every rank's gathered tensor (symmetric memory, P2P)",
                              "multicast": "multimem.st from the step kernel through one NVLS multicast address",
