@@ -558,7 +558,10 @@ int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, u
   auto bail = [&](int code) { mmz_destroy(h); return code; };
   if (cudaSetDevice(device) != cudaSuccess) return bail(fail(MMZ_ERR_CUDA, "cudaSetDevice(%d) failed", device));
   const int nv = h->hm.nv;
-  if (configure_h(h, &rc)) rc = MMZ_OK;
+  const char* force_g = getenv("MMZ_FORCE_G");  // development aid: "G,NVP" pins a lanes-per-environment instance
+  int fg = 0, fnvp = 0;
+  if (force_g && sscanf(force_g, "%d,%d", &fg, &fnvp) == 2 && fg > 0) rc = configure(h, fg, fnvp);
+  else if (configure_h(h, &rc)) rc = MMZ_OK;
   else if (rc != MMZ_OK) return bail(rc);
   else if (nv <= 4 && h->hm.nbody <= 8 && h->hm.ngeom <= 8) rc = configure(h, 8, 4);
   else if (nv <= 8) rc = configure(h, 8, 8);

@@ -468,9 +468,10 @@ struct HEnv {
   MMZ_DI void collide_item(const TLayout& L, int item, int pass) {
     int n = 0;
     unsigned hits = 0, wanted = 0xffffffffu;
-    if (pass == 1 && item < L.ng) {
+    if (pass == 1) {  // (box candidate items only carry the count)
       wanted = __reduce_or_sync(kAll, (unsigned)I(L.o_gcnt + item));
       if ((wanted & 31u) == 0) return;
+      if (item >= L.ng) wanted = 0xffffffffu;
     }
     const int base = pass == 1 ? item_base(L, item) : 0;
     if (item < L.ng) {
