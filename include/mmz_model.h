@@ -17,7 +17,7 @@ typedef float mmz_real;
 #endif
 
 #define MMZ_MAGIC 0x4D4D5A31
-#define MMZ_VERSION 4
+#define MMZ_VERSION 5
 #define MMZ_MAXBODY 16
 #define MMZ_MAXJNT 20
 #define MMZ_MAXDOF 20
@@ -57,6 +57,10 @@ typedef float mmz_real;
 #define MMZ_TERM_AGENT 0           /* any goal within threshold of obs[:dim] maze_task.py:77-81  */
 #define MMZ_TERM_OBJECT 1          /* ... of obs[3:6]                       maze_task.py:599-604 */
 #define MMZ_TERM_HOST 2
+/* forward_reward_fn of AntEnv / SwimmerEnv (reference ant.py:18-23) on the xy velocity of the step */
+#define MMZ_FWD_VNORM 0            /* forward_reward_vnorm: |v|, the default                     */
+#define MMZ_FWD_VABS 1             /* forward_reward_vabs: |vx| + |vy|                           */
+#define MMZ_FWD_HOST 2             /* any other callable: the host wrapper adds weight * fn(v)   */
 
 typedef struct mmz_model {
   int32_t magic;
@@ -87,6 +91,7 @@ typedef struct mmz_model {
   int32_t n_agent_v; /* agent qvel entries copied to obs */
   int32_t nobj; /* observed bodies spliced after obs[:3] */
   int32_t reset_kind; /* MMZ_RESET_* */
+  int32_t forward_reward_kind; /* MMZ_FWD_*: forward_reward_fn of the torque agents (ant.py:18-23,44-53) */
   int32_t nviewb; /* bodies latched for the top-down view after the observed ones: torso, then movable blocks */
   int32_t view_dim; /* 0, or 75 = 5x5x3 top-down view between the state part of obs and t (maze_env.py:353-369) */
   int32_t obj_body[8]; /* nobj observed bodies, then nviewb view bodies */
@@ -115,6 +120,7 @@ typedef struct mmz_model {
   int32_t act_limited[8];
   int32_t goal_dim[4];
   int32_t grid[144]; /* row-major, bit0 wall box (BLOCK cell), bit1 platform box, bit2 CHASM cell */
+  int32_t pad_;
   mmz_real timestep;
   mmz_real gravity[3];
   mmz_real density; /* fluid */
@@ -173,7 +179,7 @@ typedef struct mmz_model {
   mmz_real seg[64][4]; /* x1 y1 x2 y2 */
 } mmz_model;
 
-#define MMZ_MODEL_NINT 590
+#define MMZ_MODEL_NINT 592
 #define MMZ_MODEL_NREAL 1477
 
 #endif /* MMZ_MODEL_H */

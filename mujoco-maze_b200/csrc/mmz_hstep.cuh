@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
     if (!bad) {
       const float dt = T.m->timestep * T.m->frame_skip;
       const float vx = (S(L.o_qpos) - bx) / dt, vy = (S(L.o_qpos + 1) - by) / dt;
-      fwd = sqrtf(vx * vx + vy * vy);
+      // forward_reward_fn (ant.py:18-23): vnorm, vabs, or left to the host wrapper
+      const int fk = T.m->forward_reward_kind;
+      fwd = fk == MMZ_FWD_VABS ? fabsf(vx) + fabsf(vy) : fk == MMZ_FWD_HOST ? 0.f : sqrtf(vx * vx + vy * vy);
       for (int a = 0; a < L.nu; a++) { const float v = S(L.o_act + a); cc += v * v; }
       cc *= T.m->ctrl_cost_weight;
       inner = T.m->forward_reward_weight * fwd - cc;

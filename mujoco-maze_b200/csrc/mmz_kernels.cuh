@@ -217,7 +217,9 @@ struct Task : Env<G, NVP, FEAT> {
     } else if (!bad) {  // AntEnv.step / SwimmerEnv.step (ant.py:61-73, swimmer.py:37-47)
       float dt = m->timestep * m->frame_skip;
       float vx = (qpos[0] - before[0]) / dt, vy = (qpos[1] - before[1]) / dt;
-      fwd = sqrtf(vx * vx + vy * vy);
+      // forward_reward_fn (ant.py:18-23): vnorm, vabs, or left to the host wrapper
+      const int fk = m->forward_reward_kind;
+      fwd = fk == MMZ_FWD_VABS ? fabsf(vx) + fabsf(vy) : fk == MMZ_FWD_HOST ? 0.f : sqrtf(vx * vx + vy * vy);
 #pragma unroll
       for (int a = 0; a < MMZ_MAXACT; a++) cc += act[a] * act[a];
       cc *= m->ctrl_cost_weight;

@@ -2,8 +2,9 @@
 
 Step semantics baked into the kernel (STEP_TORQUE, frame_skip 5): ctrl = clamp(a),
 5 RK4 `mj_step`s, inner reward = w * |dxy / dt| - c * sum(a^2) with the raw action
-(ant.py:56-73). `forward_reward_fn` other than the default L2 norm is not
-supported in-kernel.
+(ant.py:56-73). `forward_reward_fn`: the reference's two functions are fused into the kernel
+(`forward_reward_vnorm` |v|, `forward_reward_vabs` |vx| + |vy|; ant.py:18-23); any other callable is evaluated
+by the host wrapper on the step's xy velocity (MazeEnv.step) and added to the kernel's reward.
 """
 
 from typing import Callable
@@ -21,6 +22,11 @@ def forward_reward_vabs(xy_velocity) -> float:
 
 def forward_reward_vnorm(xy_velocity) -> float:
     return np.linalg.norm(xy_velocity)
+
+
+def forward_reward_kind(fn) -> int:
+    """include/mmz_model.h MMZ_FWD_*: 0 vnorm, 1 vabs (both in-kernel), 2 = evaluated on the host."""
+    return 0 if fn is forward_reward_vnorm else 1 if fn is forward_reward_vabs else 2
 
 
 def q_inv(a):
@@ -54,8 +60,6 @@ class AntEnv(AgentModel):
         forward_reward_fn: ForwardRewardFn = forward_reward_vnorm,
     ) -> None:
         super().__init__(file_path)
-        if forward_reward_fn is not forward_reward_vnorm:
-            raise NotImplementedError("only forward_reward_vnorm is fused into the step kernel")
         self._forward_reward_weight = forward_reward_weight
         self._ctrl_cost_weight = ctrl_cost_weight
         self._forward_reward_fn = forward_reward_fn

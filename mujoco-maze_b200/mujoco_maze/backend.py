@@ -149,13 +149,32 @@ class BatchedSim:
                                       self.done.data_ptr(), self.info.data_ptr(), self._stream()))
         return self.obs, self.reward, self.done, self.info
 
+    def _buffers(self, action, obs, reward, done, info, host: bool):
+        """The C ABI takes raw addresses: a wrong dtype, shape, stride or device would be a silent out-of-bounds access."""
+        t = self.torch
+        want = (("action", action, (self.n, self.nu), t.float32), ("obs", obs, (self.n, self.obs_dim), t.float32),
+                ("reward", reward, (self.n,), t.float32), ("done", done, (self.n,), t.uint8), ("info", info, (self.n, 4), t.float32))
+        for name, x, shape, dtype in want:
+            if x is None and name == "info":
+                continue
+            if not t.is_tensor(x) or x.dtype != dtype or tuple(x.shape) != shape or not x.is_contiguous():
+                raise ValueError(f"{name}: expected a contiguous {dtype} tensor of shape {shape}, got "
+                                 f"{type(x).__name__} {getattr(x, 'dtype', None)} {tuple(getattr(x, 'shape', ()))}")
+            if host:
+                if x.device.type != "cpu" or not x.is_pinned():
+                    raise ValueError(f"{name}: step_host needs pinned host memory (tensor.pin_memory()), got {x.device}")
+            elif x.device != self.device and not (x.device.type == "cuda" and x.device.index == self.index):
+                raise ValueError(f"{name}: tensor on {x.device}, the environments live on {self.device}")
+
     def step_into(self, action, obs, reward, done, info=None):
         """Step with caller-provided output tensors (bench / multi-buffering)."""
+        self._buffers(action, obs, reward, done, info, host=False)
         self._check(self.lib.mmz_step(self._h, action.data_ptr(), obs.data_ptr(), reward.data_ptr(),
                                       done.data_ptr(), _ptr(info), self._stream()))
 
     def step_host(self, h_action, h_obs, h_reward, h_done, h_info=None):
         """End-to-end step through pinned host tensors (synchronises the stream)."""
+        self._buffers(h_action, h_obs, h_reward, h_done, h_info, host=True)
         self._check(self.lib.mmz_step_host(self._h, h_action.data_ptr(), h_obs.data_ptr(), h_reward.data_ptr(),
                                            h_done.data_ptr(), _ptr(h_info), self._stream()))
 

@@ -74,6 +74,11 @@ class MazeEnv(gym.Env):
         self._put_spin_near_agent = self._task.PUT_SPIN_NEAR_AGENT
 
         self.wrapped_env = model_cls(file_path=None, **kwargs)
+        from mujoco_maze.ant import forward_reward_kind
+
+        fwd_fn = getattr(self.wrapped_env, "_forward_reward_fn", None)
+        self._forward_kind = forward_reward_kind(fwd_fn) if fwd_fn is not None else 0
+        self._prev_xy = None  # host-evaluated forward_reward_fn: xy before the step
         self.model: MazeModel = compile_maze_model(
             model_cls,
             self._task,
@@ -83,6 +88,7 @@ class MazeEnv(gym.Env):
             restitution_coef=restitution_coef,
             forward_reward_weight=getattr(self.wrapped_env, "_forward_reward_weight", 1.0),
             ctrl_cost_weight=getattr(self.wrapped_env, "_ctrl_cost_weight", 1e-4),
+            forward_reward_kind=self._forward_kind,
             # the scalar env is wrapped by gym's TimeLimit on the host, exactly like upstream
             max_episode_steps=max_episode_steps if self.is_batched else 0,
         )
@@ -105,6 +111,12 @@ class MazeEnv(gym.Env):
             self._collision = None
         self._host_reward = int(self.model.reward_rule) == _tasks.REWARD_HOST
         self._host_term = int(self.model.term_rule) == _tasks.TERM_HOST
+        if self._auto_reset and (self._host_reward or self._host_term or self._forward_kind == 2):
+            # The kernel restarts an episode inside the launch that ends it: a termination only the host can see would
+            # never reset its environment, and after a TimeLimit reset the returned observation already belongs to the
+            # next episode, so host rules would be evaluated on the wrong state.
+            raise ValueError("auto_reset=True needs the task's reward / termination (and forward_reward_fn) to run inside "
+                             "the kernel; this task or agent defines its own in Python. Use auto_reset=False and reset(mask=done).")
 
         self.observation_space = self._get_obs_space()
         self._websock_port = websock_port
@@ -214,15 +226,26 @@ class MazeEnv(gym.Env):
         self.t = 0
         self._episode += 1
         obs = self.sim.reset(seed=(self._seed << 20) + self._episode, mask=mask)
+        if self._forward_kind == 2:
+            self._prev_xy = obs[:, :2].clone()
         obs = self._out(obs if not self.is_batched else obs.clone())
         return (obs, {}) if return_info else obs
 
-    def step(self, action):
+    def step(self, action, copy: bool = True):
+        """One MazeEnv.step (maze_env.py:448-481) of every environment in ONE kernel launch.
+
+        Batched envs return device tensors. With `copy=True` (default) they are fresh tensors the caller may keep; with
+        `copy=False` they are the engine's own output buffers, overwritten by the next `step` / `reset` (saves four
+        device-to-device copies per step for callers that consume them right away)."""
         self.t += 1
         sim = self.sim
         if not self.is_batched:
             action = np.asarray(action, dtype=np.float32).reshape(1, -1)
         obs, reward, done, info_t = sim.step(action)
+        if self.is_batched and copy:
+            obs, reward, done, info_t = obs.clone(), reward.clone(), done.clone(), info_t.clone()
+        if self._forward_kind == 2:
+            reward, info_t = self._host_forward_reward(obs, reward, info_t)
         if self._host_reward or self._host_term:
             reward, done = self._host_rules(obs, reward, done, info_t)
         has_inner = self.model.step_kind == 0  # torque agents report reward_forward / reward_ctrl
@@ -258,24 +281,62 @@ class MazeEnv(gym.Env):
         consts += [float(g.reward_scale) for g in self._task.goals]
         return consts
 
-    def _host_rules(self, obs, reward, done, info_t):
-        """User-defined MazeTask.reward / termination (README custom-task recipe): evaluated on the host.
-
-        The kernel returned the scaled inner reward (outer rule REWARD_HOST adds nothing) and
-        done without the goal test (TERM_HOST); add the Python rules per env.
-        """
+    def _host_forward_reward(self, obs, reward, info_t):
+        """A `forward_reward_fn` that is neither of the reference's two (ant.py:18-23, 44-53): the kernel left the
+        forward term out (MMZ_FWD_HOST); evaluate the callable on the step's xy velocity and add it. The callable is
+        the reference's scalar signature fn(xy_velocity[2]); a result of shape [N] for the [N, 2] batch is used as is,
+        anything else falls back to one call per environment."""
         import torch
 
-        o = obs.detach().cpu().numpy().astype(np.float64)
-        r = reward.detach().cpu().numpy().astype(np.float64)
-        d = done.detach().cpu().numpy()
-        for i in range(o.shape[0]):
-            if self._host_reward:
-                r[i] += float(self._task.reward(o[i]))
-            if self._host_term and self._task.termination(o[i]):
-                d[i] |= 1
-        return (torch.as_tensor(r, dtype=torch.float32, device=reward.device),
-                torch.as_tensor(d, dtype=torch.uint8, device=done.device))
+        xy = info_t[:, :2]
+        prev = self._prev_xy if self._prev_xy is not None else xy
+        dt = float(self.model.timestep) * int(self.model.frame_skip)
+        vel = ((xy - prev) / dt).detach().cpu().numpy().astype(np.float64)
+        fn = self.wrapped_env._forward_reward_fn
+        fwd = None
+        try:
+            out = np.asarray(fn(vel), dtype=np.float64)
+            if out.shape == (vel.shape[0],) and vel.shape[0] > 1:
+                fwd = out
+        except Exception:  # noqa: BLE001  (not written for batches)
+            fwd = None
+        if fwd is None:
+            fwd = np.array([float(fn(v)) for v in vel])
+        fwd_t = torch.as_tensor(fwd, dtype=torch.float32, device=reward.device)
+        w = float(self._inner_reward_scaling) * float(getattr(self.wrapped_env, "_forward_reward_weight", 1.0))
+        info_t = info_t.clone()
+        info_t[:, 2] = fwd_t
+        self._prev_xy = obs[:, :2].clone()
+        return reward + w * fwd_t, info_t
+
+    def _host_rules(self, obs, reward, done, info_t):
+        """User-defined MazeTask.reward / termination (README custom-task recipe, reference README.md:79-127).
+
+        The kernel returned the scaled inner reward (outer rule REWARD_HOST adds nothing) and done without the goal
+        test (TERM_HOST). A task may offer batch versions - `reward_batch(obs)` / `termination_batch(obs)`, `[N, D]`
+        device tensor in, `[N]` tensor out - which run without leaving the device; otherwise the reference's scalar
+        methods are called per environment on ONE host copy of the observations (fine for small batches; a 65 536-env
+        batch needs the batch versions)."""
+        import torch
+
+        task = self._task
+        rb, tb = getattr(task, "reward_batch", None), getattr(task, "termination_batch", None)
+        need_loop = (self._host_reward and rb is None) or (self._host_term and tb is None)
+        o = obs.detach().cpu().numpy().astype(np.float64) if need_loop else None
+        if self._host_reward:
+            if rb is not None:
+                reward = reward + torch.as_tensor(rb(obs), dtype=torch.float32, device=reward.device).reshape(-1)
+            else:
+                add = np.fromiter((float(task.reward(row)) for row in o), dtype=np.float64, count=o.shape[0])
+                reward = reward + torch.as_tensor(add, dtype=torch.float32, device=reward.device)
+        if self._host_term:
+            if tb is not None:
+                hit = torch.as_tensor(tb(obs), device=done.device).reshape(-1).to(torch.bool)
+            else:
+                hit = torch.as_tensor(np.fromiter((bool(task.termination(row)) for row in o), dtype=bool, count=o.shape[0]),
+                                      device=done.device)
+            done = done | hit.to(torch.uint8)
+        return reward, done
 
     def set_marker(self) -> None:
         """Reference maze_env.py:384-387 moves the goal sites of the MuJoCo scene before rendering. The rasteriser draws

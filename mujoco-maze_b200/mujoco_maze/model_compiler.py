@@ -673,6 +673,7 @@ def compile_maze_model(
     restitution_coef: float = 0.8,
     forward_reward_weight: float = 1.0,
     ctrl_cost_weight: float = 1e-4,
+    forward_reward_kind: int = 0,
     max_episode_steps: int = 1000,
     merge_welded: bool = True,
     legacy_capsule_volume: bool = True,
@@ -809,7 +810,7 @@ def compile_maze_model(
         frame_skip=agent.FRAME_SKIP, manual_collision=int(agent.MANUAL_COLLISION),
         collision_on=int(sc.collision_on), has_floor=int(floor is not None), elevated=int(elevated),
         reward_rule=reward_rule, term_rule=term_rule, max_episode_steps=max_episode_steps,
-        obs_dim=obs_dim, n_agent_q=naq, n_agent_v=nav, nobj=len(obs_bodies), reset_kind=reset_kind,
+        obs_dim=obs_dim, n_agent_q=naq, n_agent_v=nav, nobj=len(obs_bodies), reset_kind=reset_kind, forward_reward_kind=int(forward_reward_kind),
         obj_body=np.array(obs_bodies + view_bodies, dtype=np.int64), nviewb=len(view_bodies), view_dim=view_dim, goal_dim=np.array([g.dim for g in goals], dtype=np.int64),
         grid=grid,
         timestep=sc.timestep, gravity=sc.gravity, density=sc.density, viscosity=sc.viscosity,

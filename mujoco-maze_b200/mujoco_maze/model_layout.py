@@ -12,7 +12,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 
 MAGIC = 0x4D4D5A31  # 'MMZ1'
-VERSION = 4
+VERSION = 5
 
 CAPS = dict(
     MAXBODY=16,  # moving bodies (world excluded)
@@ -71,6 +71,7 @@ INT_FIELDS: List[Tuple[str, Tuple[int, ...], str]] = [
     ("n_agent_v", (), "agent qvel entries copied to obs"),
     ("nobj", (), "observed bodies spliced after obs[:3]"),
     ("reset_kind", (), "MMZ_RESET_*"),
+    ("forward_reward_kind", (), "MMZ_FWD_*: forward_reward_fn of the torque agents (ant.py:18-23,44-53)"),
     ("nviewb", (), "bodies latched for the top-down view after the observed ones: torso, then movable blocks"),
     ("view_dim", (), "0, or 75 = 5x5x3 top-down view between the state part of obs and t (maze_env.py:353-369)"),
     ("obj_body", (O,), "nobj observed bodies, then nviewb view bodies"),
@@ -273,6 +274,10 @@ def header_text() -> str:
         "#define MMZ_TERM_AGENT 0           /* any goal within threshold of obs[:dim] maze_task.py:77-81  */",
         "#define MMZ_TERM_OBJECT 1          /* ... of obs[3:6]                       maze_task.py:599-604 */",
         "#define MMZ_TERM_HOST 2",
+        "/* forward_reward_fn of AntEnv / SwimmerEnv (reference ant.py:18-23) on the xy velocity of the step */",
+        "#define MMZ_FWD_VNORM 0            /* forward_reward_vnorm: |v|, the default                     */",
+        "#define MMZ_FWD_VABS 1             /* forward_reward_vabs: |vx| + |vy|                           */",
+        "#define MMZ_FWD_HOST 2             /* any other callable: the host wrapper adds weight * fn(v)   */",
         "",
         "typedef struct mmz_model {",
     ]

@@ -23,8 +23,6 @@ class ReacherEnv(AgentModel):
         forward_reward_fn: ForwardRewardFn = forward_reward_vnorm,
     ) -> None:
         super().__init__(file_path)
-        if forward_reward_fn is not forward_reward_vnorm:
-            raise NotImplementedError("only forward_reward_vnorm is fused into the step kernel")
         self._forward_reward_weight = forward_reward_weight
         self._ctrl_cost_weight = ctrl_cost_weight
         self._forward_reward_fn = forward_reward_fn

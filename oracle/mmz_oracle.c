@@ -1286,7 +1286,8 @@ int ora_step(ora_env* e, const double* action, double* obs, double* reward, doub
     for (int k = 0; k < m->frame_skip && !bad; k++) bad = mj_step(e);
     double dt = m->timestep * m->frame_skip;
     double vx = (e->qpos[0] - before[0]) / dt, vy = (e->qpos[1] - before[1]) / dt;
-    fwd = sqrt(vx * vx + vy * vy);
+    /* forward_reward_fn (ant.py:18-23): vnorm, vabs, or left to the host wrapper */
+    fwd = m->forward_reward_kind == MMZ_FWD_VABS ? fabs(vx) + fabs(vy) : m->forward_reward_kind == MMZ_FWD_HOST ? 0.0 : sqrt(vx * vx + vy * vy);
     for (int a = 0; a < m->nu; a++) cc += action[a] * action[a];
     cc *= m->ctrl_cost_weight;
     inner = m->forward_reward_weight * fwd - cc;
