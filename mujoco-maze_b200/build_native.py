@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         if force or _stale(o, hdrs + [os.path.join(CSRC, "mmz_inst.cu")]):
             jobs.append(([nvcc, *NVCC_FLAGS, f"-DMMZ_G={g}", f"-DMMZ_NVP={nvp}", f"-DMMZ_FEAT={feat}", "-c",
                           os.path.join(CSRC, "mmz_inst.cu"), "-o", o], o + ".log"))
-    for nvp, box in ((14, 0), (16, 1)):
+    for nvp, box in ((14, 0), (16, 1), (4, 1)):
         h_o = os.path.join(OBJ, f"mmz_hinst_{nvp}.o")
         objs.append(h_o)
         if force or _stale(h_o, hdrs + [os.path.join(CSRC, "mmz_hinst.cu")]):

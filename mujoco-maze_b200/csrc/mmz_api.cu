@@ -49,6 +49,7 @@ typedef mmz::kernel_fn kernel_fn;
 namespace mmz {
 hkernel_fn get_hkernel_14(int mode);
 hkernel_fn get_hkernel_16(int mode);
+hkernel_fn get_hkernel_4(int mode);
 #define MMZ_DECL(g, nvp, feat) kernel_fn get_kernel_##g##_##nvp##_##feat(int mode);
 MMZ_INSTANCES(MMZ_DECL)
 #undef MMZ_DECL
@@ -259,9 +260,8 @@ bool configure_h(mmz_env* h, int* rc) {
   *rc = MMZ_OK;
   const char* kenv = getenv("MMZ_KERNEL");  // development aid: "groups" forces the lanes-per-environment kernel
   if (kenv && !strcmp(kenv, "groups")) return false;
-  if (m.step_kind != MMZ_STEP_TORQUE || m.manual_collision) return false;
   if (m.density > 0.f || m.viscosity > 0.f) return false;
-  if (m.nv < 9 || m.nv > 16) return false;  // small models are already served well by 8 lanes per environment
+  if (m.nv > 16) return false;
   int nbox = 0;
   for (int g = 0; g < m.ngeom; g++) {
     const int t = m.geom_type[g];
@@ -285,8 +285,17 @@ bool configure_h(mmz_env* h, int* rc) {
     }
   }
   const bool box = nbox > 0;
-  if (box && m.nv <= 14) return false;   // instances built: <14, no boxes> and <16, boxes>
-  if (!box && m.nv > 14) return false;
+  // instances built: <14, no boxes> (solver v2) and <16, boxes>. The second also takes the small robots with a box geom
+  // (the Point and its arrow, 3 dofs, teleport step + manual wall clamp): a step of them is bound by the LATENCY of a few
+  // long dependent chains, which the lane = environment tree phases run for 32 environments per instruction.
+  if (!box && (m.nv > 14 || m.nv < 9)) return false;
+  if (m.nv < 9) {
+    // Measured on B200 (profiles/r2_bench.md): PointUMaze 4096 envs 0.272 -> 0.239 ms, PointPush 65536 envs 5.84 -> 3.74 ms,
+    // but the single-body Point at 65536 envs 1.83 -> 2.38 ms (the lanes kernel keeps 64 of them per SM in flight).
+    bool use = m.nbody > 1 || h->n <= 16384;
+    if (const char* e = getenv("MMZ_POINT_HYBRID")) use = atoi(e) != 0;  // development aid
+    if (!use) return false;
+  }
   TLayout L;
   memset(&L, 0, sizeof L);
   L.nb = m.nbody; L.nj = m.njnt; L.nv = m.nv; L.nq = m.nq; L.nu = m.nu; L.ng = m.ngeom; L.nobj = m.nobj; L.obs_dim = m.obs_dim;
@@ -299,7 +308,7 @@ bool configure_h(mmz_env* h, int* rc) {
   L.nstate = m.nq + 2 * m.nv + 3 * L.nlatch;
   const int nitems = L.ng + nbox * (1 + 2 * 9 + (nbox - 1));  // HEnv::n_items
   if (nitems + 2 * m.nv > kMaxCTasks) return false;  // the phase C schedule of TDerived
-  const int nvp = box ? 16 : 14;  // the solver reads qacc / dir up to the instance's padded nv (zero beyond nv)
+  const int nvp = box ? (m.nv <= 4 ? 4 : 16) : 14;  // the solver reads qacc / dir up to the instance's padded nv (zero beyond nv)
   L.model_bytes = round_up(round_up((int)sizeof(mmz_model), 16) + (int)sizeof(TDerived), 16);
   int dev_smem = 0;
   if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device) != cudaSuccess) return false;
@@ -375,12 +384,12 @@ bool configure_h(mmz_env* h, int* rc) {
   h->TL = L;
   h->smem_bytes = round_up(L.model_bytes, 128) + L.nslots * HS * 4;
   for (int mode = 0; mode < 5; mode++) {
-    h->tfn[mode] = box ? mmz::get_hkernel_16(mode) : mmz::get_hkernel_14(mode);
+    h->tfn[mode] = !box ? mmz::get_hkernel_14(mode) : nvp == 4 ? mmz::get_hkernel_4(mode) : mmz::get_hkernel_16(mode);
     cudaError_t e = cudaFuncSetAttribute(h->tfn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
     if (e != cudaSuccess) { *rc = fail(MMZ_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return false; }
   }
   h->use_t = true;
-  h->G = 16; h->NVP = box ? 16 : 14; h->feat = box ? FEAT_BOX : 0; h->tpb = TW * 32; h->envs_per_sm = TE;
+  h->G = 16; h->NVP = nvp; h->feat = box ? FEAT_BOX : 0; h->tpb = TW * 32; h->envs_per_sm = TE;
   h->L.stride = L.nslots; h->L.nstate = L.nstate; h->L.model_bytes = L.model_bytes;
   return true;
 }

@@ -1,5 +1,5 @@
 // mmz_hinst.cu - hybrid kernel instances: -DMMZ_NVP=<registers per Hessian row> -DMMZ_BOX=<box geoms compiled in>
-// (14, 0: the Ant family; 16, 1: Ant with a movable block), one kernel per mode.
+// (14, 0: the Ant family; 16, 1: Ant with a movable block; 4, 1: the Point and its arrow box), one kernel per mode.
 #include "mmz_hstep.cuh"
 
 #define MMZ_HCAT_(a, b) a##b

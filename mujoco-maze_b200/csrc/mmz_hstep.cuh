@@ -6,6 +6,7 @@
 // TimeLimit truncation (__init__.py:31) and the optional in-kernel auto-reset (reset_model, ant.py:84-96).
 #pragma once
 #include <cstdio>
+#include "mmz_clamp.cuh"
 #include "mmz_hkernel.cuh"
 
 namespace mmz {
@@ -179,22 +180,51 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
 
   if (MODE == TMODE_STEP) {
     const bool auto_reset = (A.flags & T_FLAG_AUTO_RESET) != 0;
+    const bool teleport = T.m->step_kind == MMZ_STEP_TELEPORT;
     for (int a = wid; a < L.nu; a += TW) {
       const float v = real ? A.action[(size_t)env * L.nu + a] : 0.f;
-      S(L.o_ctrl + a) = v;
+      S(L.o_ctrl + a) = teleport ? 0.f : v;  // PointEnv.step never drives its motors (point.py:44-61, quirk Q16)
       S(L.o_act + a) = v;
     }
     if (wid == 0)
       for (int k = 0; k < 4; k++) cn[(L.o_cnt + TN_ITER_SUM + k) * HS + e] = 0;
     const float bx = S(L.o_qpos), by = S(L.o_qpos + 1);
     t += 1;
+    if (teleport) {  // turn, move along the new heading, clip EVERY velocity (blocks and balls too)
+      __syncthreads();
+      if (wid == 0) {
+        float ori = S(L.o_qpos + 2) + S(L.o_act + 1);
+        if (ori < -kPi) ori += 2.f * kPi;
+        else if (kPi < ori) ori -= 2.f * kPi;
+        float sn, cs;
+        sincosf(ori, &sn, &cs);
+        const float a0 = S(L.o_act);
+        S(L.o_qpos + 2) = ori;
+        S(L.o_qpos) = bx + cs * a0;
+        S(L.o_qpos + 1) = by + sn * a0;
+      }
+      for (int d = wid; d < L.nv; d += TW) S(L.o_qvel + d) = fminf(fmaxf(S(L.o_qvel + d), -T.m->vel_limit), T.m->vel_limit);
+      __syncthreads();
+    }
     bool bad = T.state_bad(L);  // mj_checkPos / mj_checkVel of the incoming state
     __syncthreads();
 #pragma unroll 1
     for (int k = 0; k < T.m->frame_skip; k++) bad = T.mj_step(L, bad);
-    // AntEnv.step / SwimmerEnv.step (ant.py:61-73, swimmer.py:37-47)
     float inner = 0.f, fwd = 0.f, cc = 0.f;
-    if (!bad) {
+    bool moved = false;
+    if (teleport) {
+      if (T.m->manual_collision) {  // maze_env.py:450-464: a move through a wall segment bounces, or is undone
+        if (wid == 0) {
+          const float old[2] = {bx, by}, nw[2] = {S(L.o_qpos), S(L.o_qpos + 1)};
+          float pos[2];
+          const bool hit = clamp_move(T.m, old, nw, pos) && !bad;
+          if (hit) { S(L.o_qpos) = pos[0]; S(L.o_qpos + 1) = pos[1]; }
+          cn[(L.o_cnt + TN_MOVED) * HS + e] = hit ? 1 : 0;
+        }
+        __syncthreads();
+        moved = cn[(L.o_cnt + TN_MOVED) * HS + e] != 0;  // set_xy -> set_state -> mj_forward refreshes xpos
+      }
+    } else if (!bad) {  // AntEnv.step / SwimmerEnv.step (ant.py:61-73, swimmer.py:37-47)
       const float dt = T.m->timestep * T.m->frame_skip;
       const float vx = (S(L.o_qpos) - bx) / dt, vy = (S(L.o_qpos + 1) - by) / dt;
       // forward_reward_fn (ant.py:18-23): vnorm, vabs, or left to the host wrapper
@@ -205,7 +235,7 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
       inner = T.m->forward_reward_weight * fwd - cc;
     }
     unsigned bits = bad ? T_UNSTABLE_BIT : 0;  // MuJoCo's mj_checkPos/Vel/Acc auto-reset: back to qpos0, zero velocity
-    bool reset_now = bad, noise = false, refresh = bad, live = true;
+    bool reset_now = bad, noise = false, refresh = bad || moved, live = true;
     float reward = 0.f, info0 = 0.f, info1 = 0.f;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
@@ -265,7 +295,8 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
       A.counters[A.npad + env] = nreset;
     }
   } else if (MODE == TMODE_FORWARD) {
-    for (int a = wid; a < L.nu; a += TW) S(L.o_ctrl + a) = real ? A.action[(size_t)env * L.nu + a] : 0.f;
+    for (int a = wid; a < L.nu; a += TW)  // (the Point's motors are never driven: point.py:44-61)
+      S(L.o_ctrl + a) = (real && T.m->step_kind != MMZ_STEP_TELEPORT) ? A.action[(size_t)env * L.nu + a] : 0.f;
     __syncthreads();
     T.forward(L, false);
     if (real) {

@@ -176,3 +176,29 @@ def test_every_registered_id_compiles_with_the_reference_shapes():
     assert n == 145
     for env_id in ("Point2Rooms-v2", "Point4Rooms-v2", "PointBilliard-v2"):  # reference tests/test_envs.py:39-50
         assert len(gym.make(env_id).unwrapped._task.goals) > 1
+
+
+def test_ant_body_masses_follow_the_mujoco_2_capsule_convention():
+    """The reference runs on MuJoCo 2.0 (mujoco-py 2.0.2.13, poetry.lock:145-146), whose compiler takes a capsule's volume
+    as pi r^2 L + pi r^3; the compiled model must reproduce the body masses that MuJoCo 2.0 reports for this geometry
+    and density (gym Ant-v2 `model.body_mass`: torso 0.32725, leg links 0.036477, ankle links 0.064911 - SURVEY.md
+    appendix A.1). `legacy_capsule_volume=True` is the default of compile_maze_model and what every parity run uses;
+    with the exact 4/3 pi r^3 caps of later MuJoCo releases the links weigh 0.039158 / 0.067592."""
+    from mujoco_maze import model_compiler as mc
+
+    assets = os.path.join(ROOT, "mujoco-maze_b200", "mujoco_maze", "assets")
+    sc = mc.parse_mjcf(os.path.join(assets, "ant.xml"))
+    legacy = mc.flatten(sc, True)["body_mass"]
+    np.testing.assert_allclose(legacy[0], 0.32725, rtol=2e-5)
+    np.testing.assert_allclose(legacy[[1, 2, 4, 5, 7, 8, 10, 11]], 0.036477, rtol=2e-5)
+    np.testing.assert_allclose(legacy[[3, 6, 9, 12]], 0.064911, rtol=2e-5)
+    exact = mc.flatten(sc, False)["body_mass"]
+    np.testing.assert_allclose(exact[[1, 3]], [0.039158, 0.067592], rtol=2e-5)
+    # the model every env id compiles to: welded links folded into their parents, same total mass, legacy convention
+    from conftest import make_model
+
+    m = make_model("AntUMaze-v0")
+    assert int(m.nbody) == 9
+    np.testing.assert_allclose(np.asarray(m.body_mass)[:9].sum(), legacy.sum(), rtol=1e-6)
+    np.testing.assert_allclose(np.asarray(m.body_mass)[0], legacy[0] + 4 * 0.036477, rtol=2e-5)
+    assert bool(m.meta.get("legacy_capsule_volume", True)) is True

@@ -39,7 +39,8 @@ def _run(model, env_id, kernel, q, v, acts):
     return outs, qq.cpu().numpy(), vv.cpu().numpy(), cfg
 
 
-@pytest.mark.parametrize("env_id", ["AntUMaze-v0", "Ant4Rooms-v0", "AntPush-v0", "AntFall-v0"])
+@pytest.mark.parametrize("env_id", ["AntUMaze-v0", "Ant4Rooms-v0", "AntPush-v0", "AntFall-v0", "PointUMaze-v0", "Point4Rooms-v0",
+                                    "PointPush-v0", "PointFall-v0"])
 def test_hybrid_and_groups_kernels_agree(env_id):
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
@@ -50,6 +51,8 @@ def test_hybrid_and_groups_kernels_agree(env_id):
     model = make_model(env_id)
     n = 200  # not a multiple of 32: exercises the padding environments of the last block
     q, v = sample_states(model, env_id, n, rng)
+    if env_id.startswith("Point"):
+        v = np.clip(v, -9, 9)
     acts = [sample_actions(model, n, rng).astype(np.float32) for _ in range(3)]
     oh, qh, vh, cfg_h = _run(model, env_id, None, q, v, acts)
     og, qg, vg, cfg_g = _run(model, env_id, "groups", q, v, acts)
@@ -64,8 +67,8 @@ def test_hybrid_and_groups_kernels_agree(env_id):
 
 
 def test_kernel_selection_per_model():
-    """Which kernel serves which model (mmz_kernel_name): the hybrid for the Ant family with and without movable blocks,
-    the lanes-per-environment kernel (8 / 16 / 32 lanes) with only the features the model needs for everything else."""
+    """Which kernel serves which model (mmz_kernel_name): the hybrid for the Ant family with and without movable blocks and
+    for the Point (small batches, or with movable blocks), the lanes-per-environment kernel (8 / 16 / 32 lanes) with only the features the model needs for everything else."""
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
@@ -73,7 +76,8 @@ def test_kernel_selection_per_model():
 
     want = {
         "AntUMaze-v0": "maze_hkernel<14,0>", "Ant4Rooms-v0": "maze_hkernel<14,0>", "AntPush-v0": "maze_hkernel<16,1>",
-        "AntFall-v0": "maze_hkernel<16,1>", "PointUMaze-v0": "maze_kernel<8,4,1>", "SwimmerUMaze-v0": "maze_kernel<8,8,2>",
+        "AntFall-v0": "maze_hkernel<16,1>", "PointUMaze-v0": "maze_hkernel<4,1>", "PointPush-v0": "maze_hkernel<16,1>",
+        "SwimmerUMaze-v0": "maze_kernel<8,8,2>",
         "ReacherUMaze-v0": "maze_kernel<8,4,7>", "AntMultiPush-v0": "maze_kernel<32,20,7>", "PointBilliard-v0": "maze_kernel<8,8,7>",
         "AntSmallBilliard-v0": "maze_kernel<32,20,7>",
     }
@@ -83,3 +87,7 @@ def test_kernel_selection_per_model():
         got[env_id] = sim.kernel_config["kernel"]
         sim.close()
     assert got == want
+    # a single-body Point in a large batch stays on the lanes kernel (64 environments in flight per SM)
+    sim = BatchedSim(make_model("PointUMaze-v0"), 32768)
+    assert sim.kernel_config["kernel"] == "maze_kernel<8,4,1>"
+    sim.close()

@@ -18,7 +18,7 @@ flags = "-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -prec-
 jobs = [(os.path.join(PKG, "csrc/mmz_api.cu"), "/tmp/dbg_api.o", [])]
 for g, n, f in INSTANCES:
     jobs.append((os.path.join(PKG, "csrc/mmz_inst.cu"), f"/tmp/dbg_{g}_{n}_{f}.o", [f"-DMMZ_G={g}", f"-DMMZ_NVP={n}", f"-DMMZ_FEAT={f}"]))
-for n, box in ((14, 0), (16, 1)):
+for n, box in ((14, 0), (16, 1), (4, 1)):
     jobs.append((os.path.join(PKG, "csrc/mmz_hinst.cu"), f"/tmp/dbg_h{n}.o", [f"-DMMZ_NVP={n}", f"-DMMZ_BOX={box}"]))
 
 
