@@ -107,6 +107,15 @@ int mmz_reset(mmz_handle h, const uint8_t* d_mask, uint64_t seed, float* d_obs, 
 int mmz_step(mmz_handle h, const float* d_action, float* d_obs, float* d_reward, uint8_t* d_done, float* d_info,
              void* stream);
 
+/* K consecutive MazeEnv.step calls in ONE host call (SURVEY section 7 "steps per launch"): d_actions is [K][N][nu], the
+ * outputs are [K][N][obs_dim] / [K][N] / [K][N] / [K][N][4] (d_info optional), step k reading / writing slice k. Same
+ * results, bit for bit, as K mmz_step calls, including TimeLimit truncation and in-kernel auto-reset in the middle of
+ * the block. The K launches are recorded once into a CUDA graph per (K, buffers) and replayed: one driver call per
+ * rollout segment - what the small robots need, whose step is ~0.2 ms (reference loop: point.py:44-61 called once per
+ * Python iteration). */
+int mmz_step_k(mmz_handle h, int K, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_done, float* d_info,
+               void* stream);
+
 /* Same step through HOST buffers: H2D of the actions, the kernel, D2H of
  * obs/reward/done/info, then a stream synchronise. This is the end-to-end
  * call a host-resident caller (the reference's numpy world) makes. Batches of

@@ -61,6 +61,12 @@ kernel_fn get_kernel(int g, int nvp, int feat, int mode) {
 }
 }  // namespace mmz
 
+struct StepGraphKey {  // everything a recorded mmz_step_k graph bakes in
+  int K;
+  const float* actions; float* obs; float* reward; uint8_t* done; float* info; int32_t* diag;
+  uint32_t flags; int env_offset; uint64_t seed; float* peer0; long long peer_row0;
+};
+
 struct mmz_env {
   int device = 0;
   int n = 0, npad = 0;
@@ -93,6 +99,9 @@ struct mmz_env {
   float tol = 2e-6f;  // Newton convergence tolerance of the hybrid kernel (fp32 round-off floor)
   TLayout TL;
   ObsPeers peers = {};  // fused observation gather (mmz_set_obs_peers)
+  cudaGraphExec_t kgraph = nullptr;  // mmz_step_k: the K launches of the last (K, buffers) combination
+  StepGraphKey kgraph_key;
+  uint64_t launches_per_kgraph = 0;
   mmz::hkernel_fn tfn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -549,7 +558,7 @@ int configure(mmz_env* h, int G, int NVP) {
 
 extern "C" {
 
-int mmz_abi_version(void) { return 6; }
+int mmz_abi_version(void) { return 7; }
 const char* mmz_last_error(void) { return g_err; }
 
 int mmz_create(const void* model_blob, size_t bytes, int num_envs, int device, uint32_t flags, mmz_handle* out) {
@@ -719,6 +728,54 @@ int mmz_step(mmz_handle h, const float* d_action, float* d_obs, float* d_reward,
   return launch(h, MODE_STEP, A, (cudaStream_t)stream);
 }
 
+int mmz_step_k(mmz_handle h, int K, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_done, float* d_info,
+               void* stream) {
+  if (!h) return fail(MMZ_ERR_INVALID, "null handle");
+  if (K < 1 || !d_actions || !d_obs || !d_reward || !d_done) return fail(MMZ_ERR_INVALID, "mmz_step_k: K >= 1 and non-null device pointers");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  // The K launches are recorded once into a CUDA graph per (K, buffers, flags) and replayed: one driver call per
+  // rollout segment instead of K (and K view launches for TOP_DOWN_VIEW tasks).
+  StepGraphKey key;
+  memset(&key, 0, sizeof key);  // (padding bytes take part in the comparison)
+  key.K = K; key.actions = d_actions; key.obs = d_obs; key.reward = d_reward; key.done = d_done; key.info = d_info;
+  key.diag = h->d_step_diag; key.flags = h->flags; key.env_offset = h->env_offset; key.seed = h->seed;
+  key.peer0 = h->peers.n ? h->peers.buf[0] : nullptr; key.peer_row0 = h->peers.row0;
+  if (!h->kgraph || memcmp(&key, &h->kgraph_key, sizeof key) != 0) {
+    if (h->kgraph) { cudaGraphExecDestroy(h->kgraph); h->kgraph = nullptr; }
+    cudaStream_t cs = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    int rc = MMZ_OK;
+    const uint64_t launches0 = h->launches;
+    cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      const size_t n = h->n;
+      for (int k = 0; k < K && rc == MMZ_OK; k++) {
+        KArgs A;
+        memset(&A, 0, sizeof A);
+        A.action = d_actions + (size_t)k * n * h->hm.nu; A.obs = d_obs + (size_t)k * n * h->hm.obs_dim;
+        A.reward = d_reward + (size_t)k * n; A.done = d_done + (size_t)k * n; A.info = d_info ? d_info + (size_t)k * n * 4 : nullptr;
+        A.seed = h->seed;
+        A.diag = h->d_step_diag;
+        rc = launch(h, MODE_STEP, A, cs);
+      }
+      e = cudaStreamEndCapture(cs, &g);
+    }
+    h->launches_per_kgraph = h->launches - launches0;
+    h->launches = launches0;  // recorded, not run
+    if (e == cudaSuccess && rc == MMZ_OK) e = cudaGraphInstantiate(&h->kgraph, g, 0);
+    if (g) cudaGraphDestroy(g);
+    cudaStreamDestroy(cs);
+    if (rc != MMZ_OK) return rc;
+    if (e != cudaSuccess) { h->kgraph = nullptr; return fail(MMZ_ERR_CUDA, "mmz_step_k: graph capture failed: %s", cudaGetErrorString(e)); }
+    h->kgraph_key = key;
+  }
+  CUDA_TRY(cudaGraphLaunch(h->kgraph, s));
+  h->launches += h->launches_per_kgraph;
+  return MMZ_OK;
+}
+
 int mmz_step_host(mmz_handle h, const float* h_action, float* h_obs, float* h_reward, uint8_t* h_done, float* h_info,
                   void* stream) {
   if (!h) return fail(MMZ_ERR_INVALID, "null handle");
@@ -873,6 +930,7 @@ void mmz_destroy(mmz_handle h) {
   cudaDeviceSynchronize();
   cudaFree(h->d_model); cudaFree(h->d_state); cudaFree(h->d_counters);
   cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_info); cudaFree(h->d_done);
+  if (h->kgraph) cudaGraphExecDestroy(h->kgraph);
   for (cudaStream_t st : h->hs) if (st) cudaStreamDestroy(st);
   for (cudaEvent_t ev : h->hev) if (ev) cudaEventDestroy(ev);
   delete h;

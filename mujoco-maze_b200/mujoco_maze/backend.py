@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_PKG_ROOT, os.environ.get("MMZ_LIB", "libmmz.so"))
 MMZ_DONE, MMZ_TRUNCATED, MMZ_UNSTABLE = 1, 2, 4
 MMZ_AUTO_RESET = 1
 LAYOUT_ENV_MAJOR, LAYOUT_SOA = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _lib = None
 
@@ -53,6 +53,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         "mmz_set_step_diag": ([vp, vp], i32),
         "mmz_reset": ([vp, vp, u64, vp, vp], i32),
         "mmz_step": ([vp, vp, vp, vp, vp, vp, vp], i32),
+        "mmz_step_k": ([vp, i32, vp, vp, vp, vp, vp, vp], i32),
         "mmz_step_host": ([vp, vp, vp, vp, vp, vp, vp], i32),
         "mmz_observe": ([vp, vp, vp], i32),
         "mmz_get_state": ([vp, i32, vp, vp, vp, vp], i32),
@@ -75,7 +76,7 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = (
-    "mmz_create", "mmz_dims", "mmz_kernel_config", "mmz_kernel_name", "mmz_set_env_offset", "mmz_set_obs_peers", "mmz_set_step_diag", "mmz_reset", "mmz_step", "mmz_step_host", "mmz_observe", "mmz_get_state",
+    "mmz_create", "mmz_dims", "mmz_kernel_config", "mmz_kernel_name", "mmz_set_env_offset", "mmz_set_obs_peers", "mmz_set_step_diag", "mmz_reset", "mmz_step", "mmz_step_k", "mmz_step_host", "mmz_observe", "mmz_get_state",
     "mmz_set_state", "mmz_forward", "mmz_render", "mmz_launch_count", "mmz_last_error", "mmz_destroy", "mmz_abi_version",
 )
 
@@ -171,6 +172,25 @@ class BatchedSim:
         self._buffers(action, obs, reward, done, info, host=False)
         self._check(self.lib.mmz_step(self._h, action.data_ptr(), obs.data_ptr(), reward.data_ptr(),
                                       done.data_ptr(), _ptr(info), self._stream()))
+
+    def step_k(self, actions, out=None):
+        """K steps in one host call (include/mmz.h: mmz_step_k): `actions` [K, N, nu] on the device. Returns
+        (obs [K, N, obs_dim], reward [K, N], done [K, N] uint8, info [K, N, 4]); pass the previous result as `out` to reuse
+        its buffers (and the recorded CUDA graph)."""
+        t = self.torch
+        if not t.is_tensor(actions) or actions.dim() != 3 or tuple(actions.shape[1:]) != (self.n, self.nu):
+            raise ValueError(f"actions: expected a [K, {self.n}, {self.nu}] tensor")
+        a = actions.to(device=self.device, dtype=t.float32).contiguous()
+        K = int(a.shape[0])
+        if out is None or out[0].shape[0] != K:
+            out = (t.empty((K, self.n, self.obs_dim), dtype=t.float32, device=self.device),
+                   t.empty((K, self.n), dtype=t.float32, device=self.device),
+                   t.empty((K, self.n), dtype=t.uint8, device=self.device),
+                   t.empty((K, self.n, 4), dtype=t.float32, device=self.device))
+        self._k_actions = a  # the graph holds its address
+        self._check(self.lib.mmz_step_k(self._h, K, a.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                        out[3].data_ptr(), self._stream()))
+        return out
 
     def step_host(self, h_action, h_obs, h_reward, h_done, h_info=None):
         """End-to-end step through pinned host tensors (synchronises the stream)."""

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Regenerates profiles/r1_parity.md from the JSON files the GPU tests write to gpurun_out/parity/ (development aid).
+"""Regenerates profiles/<round>_parity.md from the JSON files the GPU tests write to gpurun_out/parity/ (development aid).
 
-    python tools/parity_report.py [number of GPU tests in that run]
+    python tools/parity_report.py [number of GPU tests in that run] [round, default r2]
 """
 import glob
 import json
@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.chdir(ROOT)
 P = "gpurun_out/parity"
 ntests = sys.argv[1] if len(sys.argv) > 1 else "all"
+rnd = sys.argv[2] if len(sys.argv) > 2 else "r2"
 
 
 def e(x):
@@ -19,10 +20,11 @@ def e(x):
 
 
 out = [
-    "# GPU parity evidence, round 1 (B200, `pytest tests -m gpu`, JSON written by the tests to gpurun_out/parity/)",
+    f"# GPU parity evidence, round {rnd[1:]} (B200, `pytest tests -m gpu`, JSON written by the tests to gpurun_out/parity/)",
     "",
     "Comparator: the fp64 CPU restatement `oracle/mmz_oracle.c` (physics parity-UNPINNED against MuJoCo, see DESIGN.md section 4); "
-    "clamp and top-down-view goldens: the REAL reference Python code.",
+    "clamp and top-down-view goldens: the REAL reference Python code. Model convention of every run: `legacy_capsule_volume=True` "
+    "(MuJoCo 2.0 capsule volume pi r^2 L + pi r^3, pinned by tests/test_abi_and_host.py), welded bodies merged, line-search tolerance 1e-3.",
     "Teacher-forced single evaluations / steps from identical (qpos, qvel, t, action); relative errors are |gpu - oracle| / (1 + |oracle|). "
     f"{ntests} GPU tests, all green (last run of the round, final kernels; regenerate with `python tools/parity_report.py`).",
     "",
@@ -38,14 +40,15 @@ for f in sorted(glob.glob(f"{P}/forward_*.json")):
                f"{e(d['max_rel_err_same_rows'])} | {e(d['median_rel_err'])} | {d['gpu_iters_mean']:.2f} / {d['oracle_iters_mean']:.2f} | "
                f"{d['ncon_mean']:.1f} / {d['ncon_max']} |")
 out += ["", "## One `MazeEnv.step` (`mmz_step`): state, observation, reward, done", "",
-        "| env id | envs | qpos err max / p99 | qvel err max / p99 / median | reward err max | done mismatches | unstable gpu / oracle |",
-        "|---|---|---|---|---|---|---|"]
+        "| env id | envs | qpos err max / p99 | qvel err max / p99 / median | reward err max | done mismatches | flips | unstable gpu / oracle |",
+        "|---|---|---|---|---|---|---|---|"]
 for f in sorted(glob.glob(f"{P}/step_*.json")):
     d = json.load(open(f))
     out.append(f"| {d['env']} | {d['n']} | {e(d['qpos_err_max'])} / {e(d['qpos_err_p99'])} | {e(d['qvel_err_max'])} / {e(d['qvel_err_p99'])} / "
-               f"{e(d['qvel_err_median'])} | {e(d['reward_err_max'])} | {d['done_mismatch']} | {d['unstable_gpu']} / {d['unstable_oracle']} |")
+               f"{e(d['qvel_err_median'])} | {e(d['reward_err_max'])} | {d['done_mismatch']} | {d.get('flips', '-')} | {d['unstable_gpu']} / {d['unstable_oracle']} |")
 out += ["", "Large maxima with tiny p99 are environments whose active contact set flipped between fp32 and fp64 (a contact sitting at its margin); "
-        "the tests require >= 97 % of the environments inside the tolerance and exact `done` bits.", ""]
+        "`flips` counts them (velocity error > 1e-3); the tests allow at most one per env id, require exact `done` bits and positions within 1e-2 for EVERY "
+        "environment, and the tight tolerances for the rest.", ""]
 views = sorted(glob.glob(f"{P}/view_*.json"))
 if views:
     out += ["## Top-down view after one physics step (`maze_view_kernel` vs the oracle; the oracle's raster is pinned to the reference method to 1e-9)", "",
@@ -59,5 +62,5 @@ if os.path.exists(f"{P}/rollout_drift.json"):
 if os.path.exists(f"{P}/clamp_goldens.json"):
     out += ["## Wall clamp vs the real reference Python (`tests/golden/reference_python_half.json`)", "", "```",
             open(f"{P}/clamp_goldens.json").read().strip(), "```", ""]
-open("profiles/r1_parity.md", "w").write("\n".join(out))
-print("wrote profiles/r1_parity.md")
+open(f"profiles/{rnd}_parity.md", "w").write("\n".join(out))
+print(f"wrote profiles/{rnd}_parity.md")
