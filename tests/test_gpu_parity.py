@@ -510,3 +510,44 @@ def test_short_rollout_drift_report(torch_cuda, oracle_lib):
         assert np.median(drift) < 5e-3, out
     _dump("rollout_drift", out)
     print(out)
+
+
+@pytest.mark.parametrize("env_id,n", [("PointUMaze-v0", 4096), ("AntUMaze-v0", 65536), ("Ant4Rooms-v0", 65536), ("AntPush-v0", 32768)])
+def test_parity_at_the_baseline_batch_sizes(env_id, n, torch_cuda, oracle_lib):
+    """BASELINE.json's configurations at their REAL batch sizes (the other parity tests use 160-192 environments): the
+    bench's reset (seed 0), three free-running steps with the bench's action distribution, then a fourth step checked
+    against the oracle on a strided sample of 64 environments spread over the whole grid of blocks, from the state the
+    GPU itself reached. Also: no environment of the full batch is non-finite or flagged unstable."""
+    from mujoco_maze.backend import BatchedSim
+
+    torch = torch_cuda
+    model = make_model(env_id, num_envs=n)
+    sim = BatchedSim(model, n, auto_reset=True)
+    sim.reset(seed=0)
+    lo, hi = (torch.as_tensor(np.asarray(model.act_ctrlrange, np.float32)[: sim.nu, k], device="cuda") for k in (0, 1))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for _ in range(3):
+        sim.step(lo + (hi - lo) * torch.rand((n, sim.nu), device="cuda", generator=g))
+    q, v, t = (x.cpu().numpy() for x in sim.get_state())
+    a = lo + (hi - lo) * torch.rand((n, sim.nu), device="cuda", generator=g)
+    obs, rew, done, info = sim.step(a)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(obs).all()) and int(((done & 4) != 0).sum()) == 0
+    obs, rew, done, a = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), a.cpu().numpy()
+    idx = np.unique(np.concatenate([np.arange(0, n, n // 61), [1, 31, 32, n - 1]]))
+    o = oracle_lib.OracleEnv(model)
+    o.L.ora_set_warmstart(o.h, 0)   # the GPU's warm start (its previous qacc) is not part of the state we can hand over
+    worst, flips = 0.0, 0
+    for i in idx:
+        o.set_state(q[i].astype(np.float64), v[i].astype(np.float64), int(t[i]))
+        ro, rr, bits, _ = o.step(a[i].astype(np.float64))
+        e = np.abs(obs[i] - ro) / (1 + np.abs(ro))
+        if e.max() > 1e-3:
+            flips += 1
+            assert e[:3].max() <= 1e-2, (env_id, int(i), float(e.max()))
+            continue
+        worst = max(worst, float(e.max()))
+        assert abs(rew[i] - rr) <= 1e-5 + 1e-4 * abs(rr) and int(done[i]) == int(bits), (env_id, int(i))
+    _dump(f"fullsize_{env_id}", dict(env=env_id, n=n, sampled=int(len(idx)), obs_err_max=worst, flips=flips, kernel=sim.kernel_config))
+    assert flips <= 1 and worst <= 1e-3
+    sim.close()
