@@ -458,6 +458,85 @@ struct HEnv {
     for (int k = 0; k < item; k++) base += I(L.o_gcnt + k) & 31;
     return base;
   }
+  // A box candidate item (item >= ng): candidate c of box geom k - the floor (plane-box corners), a maze box or a later
+  // box geom (box-box). The narrow phase is by far the longest task of the small robots' step, so the warp that ran it
+  // in the counting pass KEEPS what it found (local memory) across the block barrier and writes it in the second pass
+  // instead of running it again (forward(): `kept`).
+  struct BoxFound { RawContact rc[8]; int n, b1, b2, other, g; float iw; };
+  MMZ_DI void box_item_find(const TLayout& L, int item, BoxFound& f) {
+    const int bc_n = box_cands(), kbox = (item - L.ng) / bc_n, cand = (item - L.ng) - kbox * bc_n;
+    const int g = dv->boxg[kbox];
+    int n = 0;
+    const int body = m->geom_body[g];
+    f.g = g; f.b1 = -1; f.b2 = body; f.other = -1; f.iw = m->geom_invweight[g];
+    if (((m->geom_contype[g] | m->geom_conaffinity[g]) & 1) && m->collision_on) {
+      const float invw = m->geom_invweight[g];
+      float gp[3], gm[9], sz[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { gp[k] = S(L.o_gpos + 3 * g + k); sz[k] = m->geom_size[g][k]; }
+#pragma unroll
+      for (int k = 0; k < 9; k++) gm[k] = S(L.o_gmat + 9 * kbox + k);
+      RawContact* rc = f.rc;
+      if (cand == 0) {  // corners below the plane, at most 4; geom1 = plane
+        if (m->has_floor) {
+          const float margin = fmaxf(m->geom_margin[g], m->floor_margin);
+          for (int c = 0; c < 8 && n < 4; c++) {
+            float loc[3] = {(c & 1 ? 1.f : -1.f) * sz[0], (c & 2 ? 1.f : -1.f) * sz[1], (c & 4 ? 1.f : -1.f) * sz[2]}, wp[3];
+            mat_vec(wp, gm, loc);
+            const float dist = wp[2] + gp[2] - m->floor_z;
+            if (dist < margin) {
+              rc[n].dist = dist;
+              rc[n].pos[0] = wp[0] + gp[0]; rc[n].pos[1] = wp[1] + gp[1]; rc[n].pos[2] = wp[2] + gp[2] - 0.5f * dist;
+              rc[n].normal[0] = 0.f; rc[n].normal[1] = 0.f; rc[n].normal[2] = 1.f;
+              rc[n].hint[0] = rc[n].hint[1] = rc[n].hint[2] = 0.f;
+              n++;
+            }
+          }
+        }
+      } else if (cand - 1 < 2 * BCELLS) {  // maze boxes; geom1 = wall (lower geom id), geom2 = this box
+        const float wallmargin = fmaxf(m->geom_margin[g], m->wall_margin);
+        float ext[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) ext[k] = fabsf(gm[3 * k]) * sz[0] + fabsf(gm[3 * k + 1]) * sz[1] + fabsf(gm[3 * k + 2]) * sz[2];
+        ext[0] += wallmargin; ext[1] += wallmargin;
+        int i0, i1, j0, j1;
+        cell_range(gp, ext, &i0, &i1, &j0, &j1);
+        const int nj = max(0, j1 - j0 + 1), ncell = nj * max(0, i1 - i0 + 1);
+        const int ci = (cand - 1) >> 1, slot = (cand - 1) & 1;
+        if (ci < ncell) {
+          const int i = i0 + ci / nj, j = j0 + ci % nj;
+          const int code = m->grid[i * m->grid_w + j];
+          if (code & (slot == 0 ? MMZ_CELL_WALL : MMZ_CELL_PLATFORM)) {
+            const float bc[3] = {j * m->cell_size - m->origin[0], i * m->cell_size - m->origin[1], slot == 0 ? m->wall_z : m->plat_z};
+            f.other = -2;
+            n = box_box(bc, dv->ident, m->wall_half, gp, gm, sz, wallmargin, rc);
+          }
+        }
+        if (cand == 1 && ncell > BCELLS) I(L.o_cnt + TN_OVERFLOW) = 1;  // the box reaches more cells than slots
+      } else {  // box against a later box geom on another moving body
+        const int k2 = kbox + 1 + (cand - 1 - 2 * BCELLS);
+        if (k2 < dv->nboxg) {
+          const int g2 = dv->boxg[k2];
+          if (moving_pair_ok(g, g2)) {
+            float gp2[3], gm2[9];
+#pragma unroll
+            for (int k = 0; k < 3; k++) gp2[k] = S(L.o_gpos + 3 * g2 + k);
+#pragma unroll
+            for (int k = 0; k < 9; k++) gm2[k] = S(L.o_gmat + 9 * k2 + k);
+            f.other = g2; f.b1 = body; f.b2 = m->geom_body[g2];
+            f.iw = invw + m->geom_invweight[g2];
+            n = box_box(gp, gm, sz, gp2, gm2, m->geom_size[g2], fmaxf(m->geom_margin[g], m->geom_margin[g2]), rc);
+          }
+        }
+      }
+    }
+    f.n = n;
+  }
+  MMZ_DI void box_item_write(const TLayout& L, int item, int base, const BoxFound& f) {
+#pragma unroll 1
+    for (int k = 0; k < f.n; k++)
+      if (base + k < L.maxcon) write_contact(L, base + k, f.rc[k], f.b1, f.b2, f.iw, f.g, f.other);
+  }
   // Collision item `item`. pass 0 counts its contacts (into o_gcnt), pass 1 writes them at the slots following those
   // of the items before it: the contact order is the item order, independent of warp timing.
   //   item < ng: sphere / capsule geom against the floor plane, the maze boxes near it and the movable box geoms;
@@ -562,75 +641,10 @@ struct HEnv {
         }
       }
     } else if (BOX) {
-      const int bc_n = box_cands(), kbox = (item - L.ng) / bc_n, cand = (item - L.ng) - kbox * bc_n;
-      const int g = dv->boxg[kbox];
-      if (((m->geom_contype[g] | m->geom_conaffinity[g]) & 1) && m->collision_on) {
-        const int body = m->geom_body[g];
-        const float invw = m->geom_invweight[g];
-        float gp[3], gm[9], sz[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) { gp[k] = S(L.o_gpos + 3 * g + k); sz[k] = m->geom_size[g][k]; }
-#pragma unroll
-        for (int k = 0; k < 9; k++) gm[k] = S(L.o_gmat + 9 * kbox + k);
-        RawContact rc[8];
-        int b1 = -1, b2 = body, other = -1;
-        float iw = invw;
-        if (cand == 0) {  // corners below the plane, at most 4; geom1 = plane
-          if (m->has_floor) {
-            const float margin = fmaxf(m->geom_margin[g], m->floor_margin);
-            for (int c = 0; c < 8 && n < 4; c++) {
-              float loc[3] = {(c & 1 ? 1.f : -1.f) * sz[0], (c & 2 ? 1.f : -1.f) * sz[1], (c & 4 ? 1.f : -1.f) * sz[2]}, wp[3];
-              mat_vec(wp, gm, loc);
-              const float dist = wp[2] + gp[2] - m->floor_z;
-              if (dist < margin) {
-                rc[n].dist = dist;
-                rc[n].pos[0] = wp[0] + gp[0]; rc[n].pos[1] = wp[1] + gp[1]; rc[n].pos[2] = wp[2] + gp[2] - 0.5f * dist;
-                rc[n].normal[0] = 0.f; rc[n].normal[1] = 0.f; rc[n].normal[2] = 1.f;
-                rc[n].hint[0] = rc[n].hint[1] = rc[n].hint[2] = 0.f;
-                n++;
-              }
-            }
-          }
-        } else if (cand - 1 < 2 * BCELLS) {  // maze boxes; geom1 = wall (lower geom id), geom2 = this box
-          const float wallmargin = fmaxf(m->geom_margin[g], m->wall_margin);
-          float ext[3];
-#pragma unroll
-          for (int k = 0; k < 3; k++) ext[k] = fabsf(gm[3 * k]) * sz[0] + fabsf(gm[3 * k + 1]) * sz[1] + fabsf(gm[3 * k + 2]) * sz[2];
-          ext[0] += wallmargin; ext[1] += wallmargin;
-          int i0, i1, j0, j1;
-          cell_range(gp, ext, &i0, &i1, &j0, &j1);
-          const int nj = max(0, j1 - j0 + 1), ncell = nj * max(0, i1 - i0 + 1);
-          const int ci = (cand - 1) >> 1, slot = (cand - 1) & 1;
-          if (ci < ncell) {
-            const int i = i0 + ci / nj, j = j0 + ci % nj;
-            const int code = m->grid[i * m->grid_w + j];
-            if (code & (slot == 0 ? MMZ_CELL_WALL : MMZ_CELL_PLATFORM)) {
-              const float bc[3] = {j * m->cell_size - m->origin[0], i * m->cell_size - m->origin[1], slot == 0 ? m->wall_z : m->plat_z};
-              other = -2;
-              n = box_box(bc, dv->ident, m->wall_half, gp, gm, sz, wallmargin, rc);
-            }
-          }
-          if (cand == 1 && ncell > BCELLS && pass == 0) I(L.o_cnt + TN_OVERFLOW) = 1;  // the box reaches more cells than slots
-        } else {  // box against a later box geom on another moving body
-          const int k2 = kbox + 1 + (cand - 1 - 2 * BCELLS);
-          if (k2 < dv->nboxg) {
-            const int g2 = dv->boxg[k2];
-            if (moving_pair_ok(g, g2)) {
-              float gp2[3], gm2[9];
-#pragma unroll
-              for (int k = 0; k < 3; k++) gp2[k] = S(L.o_gpos + 3 * g2 + k);
-#pragma unroll
-              for (int k = 0; k < 9; k++) gm2[k] = S(L.o_gmat + 9 * k2 + k);
-              other = g2; b1 = body; b2 = m->geom_body[g2];
-              iw = invw + m->geom_invweight[g2];
-              n = box_box(gp, gm, sz, gp2, gm2, m->geom_size[g2], fmaxf(m->geom_margin[g], m->geom_margin[g2]), rc);
-            }
-          }
-        }
-        if (pass == 1)
-          for (int k = 0; k < n; k++)
-            if (base + k < L.maxcon) write_contact(L, base + k, rc[k], b1, b2, iw, g, other);
-      }
+      BoxFound f;
+      box_item_find(L, item, f);
+      n = f.n;
+      if (pass == 1) box_item_write(L, item, base, f);
     }
     if (pass == 0) I(L.o_gcnt + item) = min(n, 31) | (int)hits;
   }
@@ -1408,21 +1422,48 @@ struct HEnv {
     }
     __syncthreads();
     MMZ_TICK(2);
-    // C: contact counting, mass matrix rows, smooth forces
+    // C: contact counting, mass matrix rows, smooth forces. Box candidate items keep their contacts for phase D.
     const int nit = n_items(L);
+    constexpr int KEEP = BOX ? 3 : 1;
+    BoxFound kept[KEEP];
+    int nkept = 0;
     {
 #pragma unroll 1
       for (int i = dv->c_off[wid]; i < dv->c_off[wid + 1]; i++) {
         const int t = dv->c_item[i];
-        if (t < nit) collide_item(L, t, 0);
+        if (t < nit) {
+          if (BOX && t >= L.ng && nkept < KEEP) {
+            box_item_find(L, t, kept[nkept]);
+            I(L.o_gcnt + t) = kept[nkept].n;
+            nkept++;
+          } else {
+            collide_item(L, t, 0);
+          }
+        }
         else if (t < nit + L.nv) mass_row(L, t - nit);
         else smooth_dof(L, t - nit - L.nv);
       }
     }
     __syncthreads();
     MMZ_TICK(3);
-    // D: contacts into their slots (over the slots of arrays that are dead by now, see the layout)
-    for (int t = wid; t < nit; t += TW) collide_item(L, t, 1);
+    // D: contacts into their slots (over the slots of arrays that are dead by now, see the layout): every warp writes
+    // the items it counted - the kept box items as they are, the others through a second narrow phase
+    if (!BOX) {
+      for (int t = wid; t < nit; t += TW) collide_item(L, t, 1);
+    } else {
+      int ik = 0;
+#pragma unroll 1
+      for (int i = dv->c_off[wid]; i < dv->c_off[wid + 1]; i++) {
+        const int t = dv->c_item[i];
+        if (t >= nit) continue;
+        if (BOX && t >= L.ng && ik < KEEP) {
+          if (__any_sync(kAll, kept[ik].n > 0)) box_item_write(L, t, item_base(L, t), kept[ik]);
+          ik++;
+        } else {
+          collide_item(L, t, 1);
+        }
+      }
+    }
     if (wid == TW - 1) {
       int n = 0;
 #pragma unroll 1
