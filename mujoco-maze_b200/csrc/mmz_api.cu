@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <algorithm>
 #include <new>
@@ -461,6 +462,41 @@ void make_tderived(const mmz_model& m, TDerived* d) {
   for (int k = 0; k < m.nu; k++) d->dof_act[m.act_dof[k]] |= 1 << k;
   for (int i = 0; i < m.nv; i++)
     for (int j = i; j >= 0; j = m.dof_parent[j]) { d->dof_rel[i] |= 1 << j; d->dof_rel[j] |= 1 << i; }
+  {
+    auto q2m = [](const float* q, float* R) {
+      double n = std::sqrt((double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2] + (double)q[3] * q[3]);
+      double w = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
+      const double M[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                           2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                           2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)};
+      for (int k = 0; k < 9; k++) R[k] = (float)M[k];
+    };
+    for (int b = 0; b < m.nbody; b++) {
+      q2m(m.body_iquat[b], d->iq_R[b]);
+      bool fast = m.body_parent[b] >= 0 && m.body_jntnum[b] == 1 && m.jnt_type[m.body_jntadr[b]] == MMZ_JNT_HINGE;
+      for (int c = 0; c < m.nbody; c++)  // a child on the generic path would need this body's quaternion
+        if (m.body_parent[c] == b && !(m.body_jntnum[c] == 1 && m.jnt_type[m.body_jntadr[c]] == MMZ_JNT_HINGE)) fast = false;
+      if (getenv("MMZ_NO_FAST_KIN")) fast = false;  // development aid
+      d->kin_fast[b] = fast ? 1 : 0;
+      if (!fast) continue;
+      const int j = m.body_jntadr[b];
+      float* Rb = d->kin_Rb[b];
+      q2m(m.body_quat[b], Rb);
+      double a[3] = {m.jnt_axis[j][0], m.jnt_axis[j][1], m.jnt_axis[j][2]};
+      const double an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      for (double& v : a) v /= an;
+      const double K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+          d->kin_K[b][3 * r + c] = (float)K[3 * r + c];
+          d->kin_K2[b][3 * r + c] = (float)(K[3 * r] * K[c] + K[3 * r + 1] * K[3 + c] + K[3 * r + 2] * K[6 + c]);
+        }
+      for (int r = 0; r < 3; r++) {
+        d->kin_c[b][r] = m.body_pos[b][r] + Rb[3 * r] * m.jnt_pos[j][0] + Rb[3 * r + 1] * m.jnt_pos[j][1] + Rb[3 * r + 2] * m.jnt_pos[j][2];
+        d->kin_ax[b][r] = (float)(Rb[3 * r] * a[0] + Rb[3 * r + 1] * a[1] + Rb[3 * r + 2] * a[2]);
+      }
+    }
+  }
   d->ident[0] = d->ident[4] = d->ident[8] = 1.f;
   for (int g = 0; g < MMZ_MAXGEOM; g++) d->boxord[g] = -1;
   for (int g = 0; g < m.ngeom; g++)

@@ -66,6 +66,16 @@ struct TDerived {               // appended to the model blob in device memory
   // over a cost model (a collision item is ~4 smooth-force tasks): c_item[c_off[w] .. c_off[w + 1])
   int32_t c_off[TW + 1];
   int32_t c_item[kMaxCTasks];
+  // Fast kinematics of a body with ONE hinge joint below another moving body (the Ant's 8 leg links): its pose is two
+  // 3x3 products, R = R_parent (R_body R_joint(q)) with the joint rotation in Rodrigues form I + sin K + (1 - cos) K^2,
+  // instead of a chain of three quat2mat and two quaternion products. All constants below are in the parent's frame.
+  int32_t kin_fast[MMZ_MAXBODY];   // 1: use the fast path (no child reads this body's quaternion)
+  float kin_Rb[MMZ_MAXBODY][9];    // rotation of body_quat
+  float kin_c[MMZ_MAXBODY][3];     // joint anchor: body_pos + R_body jnt_pos
+  float kin_ax[MMZ_MAXBODY][3];    // joint axis: R_body jnt_axis
+  float kin_K[MMZ_MAXBODY][9];     // cross-product matrix of jnt_axis (body frame), and its square
+  float kin_K2[MMZ_MAXBODY][9];
+  float iq_R[MMZ_MAXBODY][9];      // rotation of body_iquat (every body): world inertia = (R iq_R) diag (R iq_R)^T
   int32_t pad2[3];
   float ident[9];
   float padf[3];
@@ -166,6 +176,43 @@ struct HEnv {
     const int p = m->body_parent[b];
     float pos[3], quat[4], R[9], rf[3];
     ref(L, rf);
+    if (dv->kin_fast[b]) {  // one hinge below a moving body: matrices only (TDerived::kin_*)
+      const int j = m->body_jntadr[b], qa = m->jnt_qadr[j], d = m->jnt_dadr[j];
+      float sn, cs;
+      __sincosf(S(L.o_qpos + qa) - m->qpos0[qa], &sn, &cs);
+      const float c1 = 1.f - cs;
+      float Rj[9], Rbj[9], Rp[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) Rj[k] = ((k == 0 || k == 4 || k == 8) ? 1.f : 0.f) + sn * dv->kin_K[b][k] + c1 * dv->kin_K2[b][k];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          Rbj[3 * r + c] = dv->kin_Rb[b][3 * r] * Rj[c] + dv->kin_Rb[b][3 * r + 1] * Rj[3 + c] + dv->kin_Rb[b][3 * r + 2] * Rj[6 + c];
+      // everything above is independent of the parent
+#pragma unroll
+      for (int k = 0; k < 9; k++) Rp[k] = S(L.o_xmat + 9 * p + k);
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) R[3 * r + c] = Rp[3 * r] * Rbj[c] + Rp[3 * r + 1] * Rbj[3 + c] + Rp[3 * r + 2] * Rbj[6 + c];
+      float an[3], ax[3], off[3], cc[6];
+      mat_vec(an, Rp, dv->kin_c[b]);
+      mat_vec(ax, Rp, dv->kin_ax[b]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) an[k] += S(L.o_xpos + 3 * p + k);
+      mat_vec(off, R, m->jnt_pos[j]);
+      const float at[3] = {an[0] - rf[0], an[1] - rf[1], an[2] - rf[2]};
+      cross3(cc + 3, at, ax);
+      cc[0] = ax[0]; cc[1] = ax[1]; cc[2] = ax[2];
+#pragma unroll
+      for (int i = 0; i < 6; i++) S(L.o_cdof + 6 * d + i) = cc[i];
+#pragma unroll
+      for (int k = 0; k < 3; k++) S(L.o_xpos + 3 * b + k) = an[k] - off[k];
+#pragma unroll
+      for (int k = 0; k < 9; k++) S(L.o_xmat + 9 * b + k) = R[k];
+      return;
+    }
     if (p < 0) {
 #pragma unroll
       for (int k = 0; k < 3; k++) pos[k] = m->body_pos[b][k];
@@ -250,44 +297,12 @@ struct HEnv {
       }
     }
   }
-  // dynamic half: world spatial inertia and the forward pass of RNE (reads its own pose and the parent's velocity /
-  // bias acceleration)
-  MMZ_DI void body_dyn(const TLayout& L, int b) {
+  // The forward pass of RNE in two parts. body_vel: velocity and bias acceleration of the body from its parent's - the only
+  // part that runs DOWN a chain, a handful of multiply-adds per dof. body_frc: world spatial inertia and the inertial
+  // force I a + v x* I v - by far the longer part, and independent from body to body once velocities exist.
+  MMZ_DI void body_vel(const TLayout& L, int b) {
     const int p = m->body_parent[b];
-    float pos[3], quat[4], R[9], rf[3];
-    ref(L, rf);
-#pragma unroll
-    for (int k = 0; k < 3; k++) pos[k] = S(L.o_xpos + 3 * b + k);
-#pragma unroll
-    for (int k = 0; k < 4; k++) quat[k] = S(L.o_xquat + 4 * b + k);
-#pragma unroll
-    for (int k = 0; k < 9; k++) R[k] = S(L.o_xmat + 9 * b + k);
     const int d0 = m->body_dofadr[b], d1 = d0 + m->body_dofnum[b];
-
-    // ---- world spatial inertia about the reference point
-    float Iw[10];
-    {
-      float ip[3], qi[4], Ri[9], c[3];
-      mat_vec(ip, R, m->body_ipos[b]);
-      quat_mul(qi, quat, m->body_iquat[b]);
-      quat2mat(Ri, qi);
-#pragma unroll
-      for (int k = 0; k < 3; k++) c[k] = ip[k] + pos[k] - rf[k];
-      const float* dg = m->body_inertia[b];
-      const float mass = m->body_mass[b], cc = dot3(c, c);
-      Iw[0] = Ri[0] * Ri[0] * dg[0] + Ri[1] * Ri[1] * dg[1] + Ri[2] * Ri[2] * dg[2] + mass * (cc - c[0] * c[0]);
-      Iw[1] = Ri[3] * Ri[3] * dg[0] + Ri[4] * Ri[4] * dg[1] + Ri[5] * Ri[5] * dg[2] + mass * (cc - c[1] * c[1]);
-      Iw[2] = Ri[6] * Ri[6] * dg[0] + Ri[7] * Ri[7] * dg[1] + Ri[8] * Ri[8] * dg[2] + mass * (cc - c[2] * c[2]);
-      Iw[3] = Ri[0] * Ri[3] * dg[0] + Ri[1] * Ri[4] * dg[1] + Ri[2] * Ri[5] * dg[2] - mass * c[0] * c[1];
-      Iw[4] = Ri[0] * Ri[6] * dg[0] + Ri[1] * Ri[7] * dg[1] + Ri[2] * Ri[8] * dg[2] - mass * c[0] * c[2];
-      Iw[5] = Ri[3] * Ri[6] * dg[0] + Ri[4] * Ri[7] * dg[1] + Ri[5] * Ri[8] * dg[2] - mass * c[1] * c[2];
-      Iw[6] = mass * c[0]; Iw[7] = mass * c[1]; Iw[8] = mass * c[2];
-      Iw[9] = mass;
-#pragma unroll
-      for (int k = 0; k < 10; k++) S(L.o_iw + 10 * b + k) = Iw[k];
-    }
-
-    // ---- RNE forward: velocity and bias acceleration of the body, then its inertial force
     float v[6], a[6];
     if (p < 0) {
 #pragma unroll
@@ -322,12 +337,49 @@ struct HEnv {
 #pragma unroll
       for (int i = 0; i < 6; i++) { a[i] += sd[i] * qv; v[i] += s[i] * qv; }
     }
-    float Ia[6], Iv[6], vxIv[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { S(L.o_vel + 6 * b + k) = v[k]; S(L.o_acc + 6 * b + k) = a[k]; }
+  }
+  MMZ_DI void body_frc(const TLayout& L, int b) {
+    float pos[3], R[9], rf[3];
+    ref(L, rf);
+#pragma unroll
+    for (int k = 0; k < 3; k++) pos[k] = S(L.o_xpos + 3 * b + k);
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = S(L.o_xmat + 9 * b + k);
+    // ---- world spatial inertia about the reference point
+    float Iw[10];
+    {
+      float ip[3], Ri[9], c[3];
+      mat_vec(ip, R, m->body_ipos[b]);
+#pragma unroll
+      for (int r = 0; r < 3; r++)  // world axes of the inertial frame: R times the (constant) rotation of body_iquat
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++)
+          Ri[3 * r + cc] = R[3 * r] * dv->iq_R[b][cc] + R[3 * r + 1] * dv->iq_R[b][3 + cc] + R[3 * r + 2] * dv->iq_R[b][6 + cc];
+#pragma unroll
+      for (int k = 0; k < 3; k++) c[k] = ip[k] + pos[k] - rf[k];
+      const float* dg = m->body_inertia[b];
+      const float mass = m->body_mass[b], cc = dot3(c, c);
+      Iw[0] = Ri[0] * Ri[0] * dg[0] + Ri[1] * Ri[1] * dg[1] + Ri[2] * Ri[2] * dg[2] + mass * (cc - c[0] * c[0]);
+      Iw[1] = Ri[3] * Ri[3] * dg[0] + Ri[4] * Ri[4] * dg[1] + Ri[5] * Ri[5] * dg[2] + mass * (cc - c[1] * c[1]);
+      Iw[2] = Ri[6] * Ri[6] * dg[0] + Ri[7] * Ri[7] * dg[1] + Ri[8] * Ri[8] * dg[2] + mass * (cc - c[2] * c[2]);
+      Iw[3] = Ri[0] * Ri[3] * dg[0] + Ri[1] * Ri[4] * dg[1] + Ri[2] * Ri[5] * dg[2] - mass * c[0] * c[1];
+      Iw[4] = Ri[0] * Ri[6] * dg[0] + Ri[1] * Ri[7] * dg[1] + Ri[2] * Ri[8] * dg[2] - mass * c[0] * c[2];
+      Iw[5] = Ri[3] * Ri[6] * dg[0] + Ri[4] * Ri[7] * dg[1] + Ri[5] * Ri[8] * dg[2] - mass * c[1] * c[2];
+      Iw[6] = mass * c[0]; Iw[7] = mass * c[1]; Iw[8] = mass * c[2];
+      Iw[9] = mass;
+#pragma unroll
+      for (int k = 0; k < 10; k++) S(L.o_iw + 10 * b + k) = Iw[k];
+    }
+    float v[6], a[6], Ia[6], Iv[6], vxIv[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { v[k] = S(L.o_vel + 6 * b + k); a[k] = S(L.o_acc + 6 * b + k); }
     inert_mul(Ia, Iw, a);
     inert_mul(Iv, Iw, v);
     cross_force(vxIv, v, Iv);
 #pragma unroll
-    for (int k = 0; k < 6; k++) { S(L.o_vel + 6 * b + k) = v[k]; S(L.o_acc + 6 * b + k) = a[k]; S(L.o_frc + 6 * b + k) = Ia[k] + vxIv[k]; }
+    for (int k = 0; k < 6; k++) S(L.o_frc + 6 * b + k) = Ia[k] + vxIv[k];
   }
 
   // kinematics only (refresh of the derived arrays after a reset / set_state)
@@ -1378,12 +1430,12 @@ struct HEnv {
 #ifdef MMZ_PHASE_TIMING
     long long tick_ = clock64();
 #endif
-    // A: the kinematic trees. Pass 0: the kinematic half of the roots. Pass 1: the subtree of every level-1 body is
-    // walked by a PAIR of warps - one does the kinematic halves down the chain, its partner follows one body behind
-    // with the dynamic halves (named barrier per pair) - while the roots' warps do the roots' dynamic halves and
-    // publish them through one more named barrier. The critical path is 3 kinematic + 1 dynamic half instead of 3
-    // full body passes, and the torso's dynamic half overlaps the legs' kinematics. (Models with more chains than
-    // warp pairs walk every chain in one warp: A_BOTH.)
+    // A: the kinematic trees. Pass 0: pose and motion axes of the roots (and, on the idle warps, the joint-limit rows).
+    // Pass 1: the roots' warps compute the roots' velocities (published through a named barrier), then their inertial forces; the subtree of every level-1 body is walked by a PAIR of warps: one runs pose +
+    // velocity down the chain - the only dependent work - and the inertial force of the LAST body; its partner follows one
+    // body behind with the inertial forces of the others (named barrier per pair), while the roots' warps do the roots'
+    // inertial forces. Critical path for the Ant: 2 short kinematic steps + 1 inertial force, instead of 3 full body passes.
+    // (Models with more chains than warp pairs walk every chain in one warp: A_BOTH.)
     {
       const int kind1 = dv->walk_kind[wid], bar = dv->walk_bar[wid];
 #pragma unroll 1
@@ -1397,12 +1449,15 @@ struct HEnv {
 #pragma unroll 1
           for (int i = i0; i < i1; i += roots ? TW : 1) {
             const int b = list[i];
+            const bool last = !roots && i == i1 - 1;
             if (kind == A_KIN || kind == A_PAIR_KIN || kind == A_BOTH) body_kin(L, b);
-            if (kind == A_PAIR_KIN || kind == A_PAIR_DYN) named_sync(bar, 64);
-            if (kind == A_PAIR_DYN && i == i0) named_sync(15, dv->walk_root_count);  // the roots' velocities exist
-            if (kind != A_KIN && kind != A_PAIR_KIN) body_dyn(L, b);
+            // the roots' velocities are computed in pass 1, beside the first kinematic step of the chains that wait for them
+            if (kind == A_ROOTDYN) { body_vel(L, b); if (i + TW >= i1) named_arrive(15, dv->walk_root_count); }
+            if (kind == A_PAIR_KIN && i == i0) named_sync(15, dv->walk_root_count);
+            if (kind == A_PAIR_KIN || kind == A_BOTH) body_vel(L, b);
+            if ((kind == A_PAIR_KIN || kind == A_PAIR_DYN) && !last) named_sync(bar, 64);
+            if (kind == A_ROOTDYN || kind == A_BOTH || (kind == A_PAIR_DYN && !last) || (kind == A_PAIR_KIN && last)) body_frc(L, b);
           }
-          if (kind == A_ROOTDYN) named_arrive(15, dv->walk_root_count);
         }
         if (pass == 0)  // in the shadow of the roots' kinematics (the last warps first: the roots are on the first ones)
           for (int d = TW - 1 - wid; d < L.nv; d += TW) limit_rows_t(L, d);
