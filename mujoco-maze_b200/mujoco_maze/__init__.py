@@ -22,7 +22,7 @@ from mujoco_maze.point import PointEnv  # noqa: E402
 from mujoco_maze.reacher import ReacherEnv  # noqa: E402
 from mujoco_maze.swimmer import SwimmerEnv  # noqa: E402
 
-__version__ = "0.2.0+b200.r1"
+__version__ = "0.2.0+b200.r2"
 
 MAX_EPISODE_STEPS = 1000  # reference __init__.py:31,47,76
 
@@ -59,6 +59,25 @@ def _register_all() -> None:
 
 
 _register_all()
+
+
+def make(env_id: str, **kwargs):
+    """`gym.make` for this package's ids that is safe for BATCHED environments under the real gym.
+
+    A batched environment (`num_envs=N`) counts its TimeLimit steps per environment inside the kernel and returns tensors;
+    gym's own scalar `TimeLimit` wrapper (which `gym.make` adds from the registered `max_episode_steps`) evaluates
+    `not done` on them and fails. The in-repo shim skips the wrapper for batched environments; with the real gym
+    installed, build them through this function, which constructs the registered entry point directly."""
+    if kwargs.get("num_envs") is None:
+        return gym.make(env_id, **kwargs)
+    spec = gym.spec(env_id) if hasattr(gym, "spec") else gym.envs.registry.spec(env_id)
+    merged = dict(getattr(spec, "kwargs", None) or getattr(spec, "_kwargs", None) or {})
+    merged.update(kwargs)
+    from mujoco_maze.maze_env import MazeEnv
+
+    env = MazeEnv(**merged)
+    env.spec = spec
+    return env
 
 
 def install_gym_shim() -> None:

@@ -202,3 +202,21 @@ def test_ant_body_masses_follow_the_mujoco_2_capsule_convention():
     np.testing.assert_allclose(np.asarray(m.body_mass)[:9].sum(), legacy.sum(), rtol=1e-6)
     np.testing.assert_allclose(np.asarray(m.body_mass)[0], legacy[0] + 4 * 0.036477, rtol=2e-5)
     assert bool(m.meta.get("legacy_capsule_volume", True)) is True
+
+
+def test_package_make_builds_batched_envs_without_a_scalar_timelimit(monkeypatch):
+    """With the real gym installed `gym.make` would wrap a batched environment in gym's scalar TimeLimit (whose `not done`
+    fails on tensors). `mujoco_maze.make` builds batched environments from the registered spec directly; simulated here by a
+    `gym.make` that always wraps."""
+    import mujoco_maze
+    from mujoco_maze import gym
+
+    def wrapping_make(env_id, **kw):
+        return gym.wrappers.TimeLimit(gym.spec(env_id).make(**kw), 1000)
+
+    monkeypatch.setattr(mujoco_maze.gym, "make", wrapping_make)
+    scalar = mujoco_maze.make("PointUMaze-v0")
+    assert type(scalar).__name__ == "TimeLimit"                       # reference-shaped env: as upstream
+    batched = mujoco_maze.make("PointUMaze-v0", num_envs=8)
+    assert type(batched).__name__ == "MazeEnv" and batched.is_batched and batched.spec.id == "PointUMaze-v0"
+    assert int(batched.model.max_episode_steps) == 1000              # counted inside the kernel instead
