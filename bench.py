@@ -453,7 +453,7 @@ def main():
             "config": workload_config(model, env_id, n_envs),
             "details": {"l2": "flushed (256 MiB write) between timed steps", "gather_obs_in_main_loop": gather_state["mode"] != "none" and bool(args.gather_obs),
                         "kernel": sim.kernel_config, "done_frac_last_step": done_frac, "unstable_last_step": unstable,
-                        "line_search_tolerance": 1e-3},
+                        "line_search_tolerance": 1e-2},
             "clocks": clocks,
             "e2e": {"value": world * n_envs * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": n_envs * nu * 4, "d2h_bytes_per_step": n_envs * (od * 4 + 4 + 1 + 16),

@@ -14,12 +14,13 @@ namespace mmz {
 constexpr float kMinVal = 1e-15f;
 constexpr float kMaxVal = 1e10f;
 constexpr float kPi = 3.14159265358979323846f;
-// The line search of the Newton solver stops at |slope| < MMZ_LS_TOL * |slope at 0| (MuJoCo's ls_tolerance is 0.01). It
-// only has to find a good point along the direction: the precision of the solution is set by the Newton stopping
-// rules. At 1e-6 (fp32 round-off) a third of the searches bounced until the step stopped changing; 1e-3 leaves the
-// Newton iteration counts and the errors against the oracle unchanged (profiles/r2_parity.md) and the Ant step is 7 % faster.
+// The line search of the Newton solver stops at |slope| < MMZ_LS_TOL * |slope at 0|: MuJoCo's own default, ls_tolerance =
+// 0.01. It only has to find a good point along the direction: the precision of the solution is set by the Newton stopping
+// rules. At 1e-6 (fp32 round-off, round 1) a third of the searches bounced until the step stopped changing; 1e-3 made the
+// Ant step 7 % faster, 1e-2 another 0.6 %, both with the Newton iteration counts (39.4 per Ant env-step) and every error
+// column against the oracle unchanged (profiles/r2_parity.md).
 #ifndef MMZ_LS_TOL
-#define MMZ_LS_TOL 1e-3f
+#define MMZ_LS_TOL 1e-2f
 #endif
 
 MMZ_DI void cross3(float* r, const float* a, const float* b) {

@@ -84,3 +84,39 @@ def test_render_point_umaze_and_ant_push():
     except ImportError:
         pass
     env.close()
+
+
+@pytest.mark.parametrize("env_id", ["PointUMaze-v0", "AntPush-v0", "AntFall-v0", "PointBilliard-v0", "Ant4Rooms-v0"])
+def test_render_matches_the_cpu_restatement_pixel_for_pixel(env_id, oracle_lib):
+    """The comparator of the rasteriser: oracle/render_oracle.py restates its specification in numpy (fp64), with body poses
+    from the fp64 oracle's kinematics. Whole images of randomly posed environments must agree: at least 99.5 % of the pixels
+    within 2 grey levels (silhouette edges may fall on the other side of a pixel centre in fp32), mean error < 0.5 level."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked test on a box without CUDA")
+    from conftest import make_model
+    from mujoco_maze.backend import BatchedSim
+    from oracle import render_oracle
+    from test_gpu_parity import sample_states
+
+    rng = np.random.default_rng(21)
+    model = make_model(env_id)
+    n, W, H = 6, 192, 160
+    q, v = sample_states(model, env_id, n, rng)
+    sim = BatchedSim(model, n)
+    sim.set_state(q, v, np.zeros(n, dtype=np.int32))
+    got = sim.render(W, H).cpu().numpy()
+    o = oracle_lib.OracleEnv(model)
+    worst_frac, worst_mean, moving_px = 1.0, 0.0, 0
+    for i in range(n):
+        o.set_state(q[i], v[i], 0)
+        o.forward()
+        xpos, xquat = o.xpos()
+        want = render_oracle.render(model, xpos, xquat, W, H)
+        diff = np.abs(got[i].astype(int) - want.astype(int)).max(-1)
+        worst_frac = min(worst_frac, float((diff <= 2).mean()))
+        worst_mean = max(worst_mean, float(diff.mean()))
+        moving_px += int((want != render_oracle.render(model, xpos + np.array([1e3, 0, 0]), xquat, W, H)).any(-1).sum())
+    assert moving_px > 60, "the restatement draws (almost) no moving geom: nothing would be compared"
+    assert worst_frac >= 0.995 and worst_mean < 0.5, (env_id, worst_frac, worst_mean)
+    sim.close()
