@@ -367,6 +367,48 @@ bool configure_h(mmz_env* h, int* rc) {
     }
     if (maxcon < 10) return false;  // does not fit: use the lanes-per-environment kernel
     L.maxcon = maxcon;
+  } else if (!getenv("MMZ_BOX_V1_LAYOUT")) {
+    // Solver v3 (mmz_hkernel.cuh: solve_g3). In front: what stays live while the solver iterates. Then [A] the arrays the
+    // solver view has loaded into registers by its block barrier, or that are dead by then (motion axes, mass matrix,
+    // smooth forces, geom poses, body velocities, contact counts, rotation matrices): the natural-order area - per
+    // environment a pool of `nj` Jacobian entries, (force, weights) pairs and the 16 Hessian rows - OVERLAYS them and
+    // runs on into its own extension. Last [B] the arrays that are dead once mass matrix and smooth forces exist
+    // (quaternions, inertias, bias accelerations and forces): the contact records overlay THOSE, as before.
+    L.v3 = 1;
+    L.cstride = K3_STRIDE;
+    L.o_dir = take(nvp);
+    L.o_nat = o = round_up(o, 4);
+    L.o_cdof = take(6 * L.nv);
+    L.o_M = take(L.nv * L.ldm);
+    L.o_smooth = take(L.nv);
+    L.o_obs = take(L.obs_core);
+    L.o_gpos = take(3 * L.ng); L.o_gax = take(3 * L.ng); L.o_gmat = take(nbox > 0 ? 9 * nbox : 1);
+    L.o_vel = take(6 * L.nb);
+    L.o_gcnt = take(nitems);
+    L.o_xmat = take(9 * L.nb);
+    const int a_end = o;
+    const int tail = 4 * L.nb + 10 * L.nb + 10 * L.nb + 6 * L.nb + 6 * L.nb + 6 * L.nb;  // xquat, iw, ic, acc, frc, fsub
+    const int static_smem = 256 + 16;  // mbarrier (+ the dummy scratch of the first solver)
+    const int avail = (dev_smem - round_up(L.model_bytes, 128) - static_smem) / (HS * 4);  // slots per environment
+    const int maxcon = std::min(32, 16 + 8 * nbox);  // two trips of 16 lanes
+    const int hq = (16 * (nvp + 1) + 3) / 4;        // float4s of the 16 Hessian rows
+    int nj = 192;
+    for (; nj >= 48; nj -= 8) {
+      L.es = nj + 2 * maxcon + hq;
+      const int nat_bytes = (TE * L.es + 1) * 16;
+      const int tail0 = std::max(a_end, L.o_nat + (nat_bytes + HS * 4 - 1) / (HS * 4));
+      L.nslots = tail0 + std::max(tail, maxcon * L.cstride);
+      if (L.nslots <= avail) {
+        o = tail0;
+        break;
+      }
+    }
+    if (nj < 48) return false;  // does not fit: use the lanes-per-environment kernel
+    L.njac = nj;
+    L.maxcon = maxcon;
+    L.o_con = o;
+    L.o_xquat = take(4 * L.nb); L.o_iw = take(10 * L.nb); L.o_ic = take(10 * L.nb);
+    L.o_acc = take(6 * L.nb); L.o_frc = take(6 * L.nb); L.o_fsub = take(6 * L.nb);
   } else {
     L.o_gpos = take(3 * L.ng); L.o_gax = take(3 * L.ng); L.o_gmat = take(nbox > 0 ? 9 * nbox : 1);
     L.o_cdof = take(6 * L.nv);

@@ -97,6 +97,7 @@ struct TLayout {
   // workspace, whose arrays are all dead while the solver runs.
   int v2, o_nat, jes, fa_off;  // first slot (multiple of 4); float4s per environment of the Jacobian area; float4 offset of FA
   int topo;                    // 1: the dof tree is the Ant's (free root + 2-dof chains): sparse elimination order (elim_solve2)
+  int v3, njac, es;            // solver v3 (box instances): float4 Jacobian entries per environment; float4s per environment of its natural area
 };
 
 struct TArgs {
@@ -139,7 +140,8 @@ __device__ unsigned long long g_wsolve[16], g_wwait[16];  // per warp of block 0
 // replace bodies by signed dof masks and the temporaries by (mu, D, aref[4]); once the Jacobian is stored, point and
 // frame are dead and J a - aref of the four pyramid rows takes their place.
 enum { K_POS = 0, K_N = 3, K_T1 = 6, K_BODY1 = 9, K_BODY2 = 10, K_MPOS = 9, K_MNEG = 10, K_MU = 11, K_D = 12, K_AREF = 13,
-       K_DIST = 13, K_INVW = 14, K_GEOM = 15, K_OTHER = 16, K_JAR = 0, K_STRIDE = 17 };
+       K_DIST = 13, K_INVW = 14, K_GEOM = 15, K_OTHER = 16, K_JAR = 0, K_STRIDE = 17,
+       K3_JV = 4, K3_JOFF = 17, K3_STRIDE = 19 };  // solver v3: J dir per pyramid row (over the dead point / normal), offset of the contact's Jacobian entries
 static __device__ __noinline__ void write_contact_record2(float* c, const RawContact& rc, int b1, int b2, float iw, int g, int other);
 
 // one out-of-line copy of the record writer (it has several call sites); `c` points at element (slot 0, env) of the
@@ -149,12 +151,18 @@ static __device__ __noinline__ void write_contact_record(float* c, const RawCont
 template <int NVP, int BOX>
 struct HEnv {
   static constexpr bool V2 = BOX == 0;  // which solver (and contact record) the instance uses
+#ifdef MMZ_BOX_V1
+  static constexpr bool V3 = false;     // (development aid: the first solver for the box instances)
+#else
+  static constexpr bool V3 = BOX != 0;  // box instances: the stored Jacobian on each contact's own dofs (solve_g3)
+#endif
   const mmz_model* m;
   const TDerived* dv;
   float* sm;
   float4* jsc;              // [32 environments][16 dofs] scratch: contact Jacobian columns during the Hessian build (BOX)
   float4* jg;               // solver v2: this lane's environment in the Jacobian area, [contact][NVP + 1] float4
   float4* fg;               // solver v2: its per-contact (force, Hessian weights) pairs, [contact][2] float4
+  float* hg;                // solver v3: this lane's row of the contact part of the Hessian, accumulated in shared memory
   int e, wid;               // tree view: lane = environment e; warp wid takes items wid, wid + 16, ...
   int genv, lane, gshift;   // solver view: environment wid + 16 * (laneid / 16), lane = dof
   float limD[2], limA[2];   // this lane's joint-limit rows (solver view)
@@ -492,7 +500,7 @@ struct HEnv {
   // stores a narrow-phase record into contact slot `slot` (layout C_* of mmz_layout.h); the normal points
   // from body b1 (geom1) to body b2 (geom2), -1 = world
   MMZ_DI void write_contact(const TLayout& L, int slot, const RawContact& rc, int b1, int b2, float iw, int g, int other) {
-    if (V2) {
+    if (V2 || V3) {
       write_contact_record2(sm + (L.o_con + slot * L.cstride) * HS + e, rc, b1, b2, iw, g, other);
     } else {
       float par[9];
@@ -1366,6 +1374,269 @@ struct HEnv {
 #endif
   }
 
+  // ================================================================== solver v3 (the box instances)
+  // Solver v2's scheme where contacts are many (a pushed block rests on four corners, touches walls with up to eight points)
+  // and most of them move few dofs (the block's two slides; an ant leg's chain of eight): the Jacobian of contact c is
+  // stored COMPRESSED, one float4 per dof of its mask, at entries [off_c, off_c + popc(mask_c)) of a per-environment pool
+  // (off_c = exclusive scan over the contacts, lane = contact). Passes over the contacts (lane = contact, 16 per trip) walk
+  // the bits of their mask; passes over the dofs find their entry at rank(lane in mask). The contact part of the Hessian
+  // row is accumulated in shared memory (dynamic column index), over the dofs of the mask only, then added to the
+  // mass-matrix row in registers. Line-search rows of the contacts stay in their records (any number of contacts).
+  MMZ_DI int cmask(int cs) const { return __float_as_int(W_(cs + K_MPOS)) | __float_as_int(W_(cs + K_MNEG)); }
+  MMZ_DI void build_jac3(const TLayout& L, const float (&cd)[6], int ncon, int ncw) {
+    int total = 0;
+#pragma unroll 1
+    for (int t0 = 0; t0 < ncw; t0 += 16) {  // offsets: lane = contact
+      const int c = t0 + lane, cs = L.o_con + c * L.cstride;
+      const bool valid = c < ncon;
+      const int cnt = valid ? __popc(cmask(cs)) : 0;
+      int incl = cnt;
+#pragma unroll
+      for (int off = 1; off < 16; off <<= 1) { const int v = __shfl_up_sync(kAll, incl, off, 16); if (lane >= off) incl += v; }
+      const int excl = incl - cnt + total;
+      if (valid) {
+        if (excl + cnt > L.njac) {  // the pool is full: the contact is dropped (and the overflow reported)
+          W_(cs + K_MPOS) = __int_as_float(0); W_(cs + K_MNEG) = __int_as_float(0);
+          IW(L.o_cnt + TN_OVERFLOW) = 1;
+        }
+        IW(cs + K3_JOFF) = min(excl, L.njac);
+      }
+      total += __shfl_sync(kAll, incl, 15, 16);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int c = 0; c < ncw; c++) {  // entries: lane = dof
+      const int cs = L.o_con + c * L.cstride;
+      const int mp = __float_as_int(W_(cs + K_MPOS)), mn = __float_as_int(W_(cs + K_MNEG)), mask = mp | mn;
+      const float s = (float)(mp >> lane & 1) - (float)(mn >> lane & 1);
+      float p[3], fr[9], wxp[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) p[k] = W_(cs + K_POS + k);
+#pragma unroll
+      for (int k = 0; k < 6; k++) fr[k] = W_(cs + K_N + k);
+      cross3(fr + 6, fr, fr + 3);
+      cross3(wxp, cd, p);
+      const float v[3] = {s * (cd[3] + wxp[0]), s * (cd[4] + wxp[1]), s * (cd[5] + wxp[2])};
+      const float mu = W_(cs + K_MU);
+      const float jn = dot3(fr, v), jt1 = mu * dot3(fr + 3, v), jt2 = mu * dot3(fr + 6, v);
+      if (c < ncon && (mask >> lane & 1))
+        jg[IW(cs + K3_JOFF) + __popc(mask & ((1 << lane) - 1))] = make_float4(jn, jt1, jt2, fabsf(jn) + fabsf(jt1) + fabsf(jt2));
+    }
+  }
+  // lane = contact (16 per trip): J x over the dofs of the contact's mask. which 0: x = qacc -> J a - aref, force and
+  // Hessian weights of the active rows; which 1: x = direction -> J dir per pyramid row into the record
+  MMZ_DI void contact_pass3(const TLayout& L, int xoff, int ncon, int ncw, int which) {
+#pragma unroll 1
+    for (int t0 = 0; t0 < ncw; t0 += 16) {
+      const int c = t0 + lane;
+      if (c >= ncw) continue;
+      float4 F = make_float4(0.f, 0.f, 0.f, 0.f), Wt = F;
+      if (c < ncon) {
+        const int cs = L.o_con + c * L.cstride;
+        const float4* jr = jg + IW(cs + K3_JOFF);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, sa = 0.f;
+#pragma unroll 1
+        for (int bits = cmask(cs); bits; bits &= bits - 1) {
+          const float4 j = *jr++;
+          const float x = W_(xoff + __ffs(bits) - 1);
+          s0 = fmaf(j.x, x, s0); s1 = fmaf(j.y, x, s1); s2 = fmaf(j.z, x, s2); sa = fmaf(j.w, fabsf(x), sa);
+        }
+        if (which == 1) {
+          W_(cs + K3_JV) = s0 + s1; W_(cs + K3_JV + 1) = s0 - s1; W_(cs + K3_JV + 2) = s0 + s2; W_(cs + K3_JV + 3) = s0 - s2;
+          continue;
+        }
+        const float r0 = W_(cs + K_AREF), r1 = W_(cs + K_AREF + 1), r2 = W_(cs + K_AREF + 2), r3 = W_(cs + K_AREF + 3);
+        const float D = W_(cs + K_D);
+        const float j0 = s0 + s1 - r0, j1 = s0 - s1 - r1, j2 = s0 + s2 - r2, j3 = s0 - s2 - r3;
+        W_(cs + K_JAR) = j0; W_(cs + K_JAR + 1) = j1; W_(cs + K_JAR + 2) = j2; W_(cs + K_JAR + 3) = j3;
+        const float a0 = j0 < 0.f, a1 = j1 < 0.f, a2 = j2 < 0.f, a3 = j3 < 0.f;
+        const float f0 = a0 * D * j0, f1 = a1 * D * j1, f2 = a2 * D * j2, f3 = a3 * D * j3;
+        const float bound = sa + fmaxf(fmaxf(fabsf(r0), fabsf(r1)), fmaxf(fabsf(r2), fabsf(r3)));
+        F = make_float4(f0 + f1 + f2 + f3, f0 - f1, f2 - f3, D * bound * (a0 + a1 + a2 + a3));
+        Wt = make_float4(D * (a0 - a1), D * (a2 - a3), D * (a0 + a1), D * (a2 + a3));
+      }
+      if (which == 0) { fg[2 * c] = F; fg[2 * c + 1] = Wt; }
+    }
+  }
+  // derivative and curvature of the cost along the direction from the rows of this lane: its two joint-limit rows
+  // (registers) and the pyramid rows r = lane, lane + 16, ... of the contacts (records); `fl`: a row changed sides
+  MMZ_DI void ls_rows3(const TLayout& L, int ncon, const float (&ljar)[2], float dr, float alpha, float* g, float* h, bool* fl) const {
+    float gg = 0.f, hh = 0.f;
+    bool f = false;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const float jv = s == 0 ? dr : -dr, x = ljar[s] + alpha * jv;
+      if (limD[s] > 0.f && x < 0.f) { gg += limD[s] * x * jv; hh += limD[s] * jv * jv; }
+      f |= limD[s] > 0.f && (x < 0.f) != (ljar[s] < 0.f);
+    }
+#pragma unroll 1
+    for (int r = lane; r < 4 * ncon; r += 16) {
+      const int cs = L.o_con + (r >> 2) * L.cstride;
+      const float jv = W_(cs + K3_JV + (r & 3)), jar = W_(cs + K_JAR + (r & 3)), x = jar + alpha * jv, D = W_(cs + K_D);
+      if (x < 0.f) { gg += D * x * jv; hh += D * jv * jv; }
+      f |= (x < 0.f) != (jar < 0.f);
+    }
+    *g = gg; *h = hh; *fl = f;
+  }
+  MMZ_DI void solve_g3(const TLayout& L, bool warmstart) {
+    const int nv = L.nv;
+    const bool me = lane < nv;
+    const unsigned limbits = gballot(limD[0] > 0.f || limD[1] > 0.f);
+    float mrow[NVP];  // this lane's row of the mass matrix (zero outside its sparsity pattern and outside the model)
+    const int rel = me ? dv->dof_rel[lane] : 0;
+#pragma unroll
+    for (int k = 0; k < NVP; k++) mrow[k] = (rel >> k & 1) ? W_(L.o_M + lane * L.ldm + k) : 0.f;
+    const float sm_ = me ? W_(L.o_smooth + lane) : 0.f;
+    int ncon, ncw;
+    {
+      float cd[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) cd[k] = me ? W_(L.o_cdof + 6 * lane + k) : 0.f;
+      // the natural area overlays the mass matrix, the motion axes and every other array the solver view has read by now
+      __syncthreads();
+      ncon = IW(L.o_cnt + TN_CON);
+      ncw = max(ncon, __shfl_xor_sync(kAll, ncon, 16));  // the two environments of the warp
+#pragma unroll
+      for (int k = 0; k < NVP; k++) hg[k] = 0.f;
+      build_jac3(L, cd, ncon, ncw);
+    }
+    const bool constrained = ncon > 0 || limbits != 0;
+    float al = (warmstart && me) ? W_(L.o_qacc + lane) : 0.f;
+    if (!(fabsf(al) < kMaxVal)) al = 0.f;  // a blown-up environment restarts from zero
+    if (me) W_(L.o_qacc + lane) = al;
+    const int nlim = __popc(gballot(limD[0] > 0.f)) + __popc(gballot(limD[1] > 0.f));
+    if (lane == 0) {
+      IW(L.o_cnt + TN_ITER) = 0; IW(L.o_cnt + TN_LIM) = nlim;
+      IW(L.o_cnt + TN_CON_MAX) = max(IW(L.o_cnt + TN_CON_MAX), ncon);
+    }
+    __syncwarp();
+    bool done = false;
+    float Ma = 0.f, Mabs = 0.f;  // (M qacc)[lane] and the magnitude of its terms, updated with every step
+#pragma unroll
+    for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_qacc + k); Ma += t; Mabs += fabsf(t); }
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+    for (int it = 0; it < kTMaxNewton; it++) {
+      float grad = Ma - sm_, dadd = 0.f;
+      float mag = Mabs + fabsf(sm_);
+      float ljar[2];
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const float sign = s == 0 ? 1.f : -1.f;
+        ljar[s] = sign * al - limA[s];
+        if (limD[s] > 0.f && ljar[s] < 0.f) {
+          grad += limD[s] * ljar[s] * sign;
+          mag += limD[s] * (fabsf(al) + fabsf(limA[s]));
+          dadd += limD[s];
+        }
+      }
+      contact_pass3(L, L.o_qacc, ncon, ncw, 0);
+      __syncwarp();
+#pragma unroll 1
+      for (int c = 0; c < ncw; c++) {  // gradient J^T f: this lane's entry of every contact that moves its dof
+        const int cs = L.o_con + c * L.cstride;
+        const unsigned mask = c < ncon ? (unsigned)cmask(cs) : 0u;
+        if (mask >> lane & 1) {
+          const float4 j = jg[IW(cs + K3_JOFF) + __popc(mask & lt)], F = fg[2 * c];
+          grad += j.x * F.x + j.y * F.y + j.z * F.z;
+          mag = fmaf(j.w, F.w, mag);
+        }
+      }
+      if (gballot(me && fabsf(grad) > tol * mag + 1e-30f) == 0) done = true;
+      if (__all_sync(kAll, done)) break;
+#pragma unroll 1
+      for (int c = 0; c < ncw; c++) {  // contact part of the Hessian row, in shared memory, over the dofs of the mask
+        const float4 Wt = fg[2 * c + 1];
+        const float wnn = Wt.z + Wt.w;
+        if (!__any_sync(kAll, wnn != 0.f)) continue;  // no active row in this contact, in either environment
+        const int cs = L.o_con + c * L.cstride;
+        const unsigned mask = (c < ncon && wnn != 0.f) ? (unsigned)cmask(cs) : 0u;
+        if (mask >> lane & 1) {
+          const float4* jr = jg + IW(cs + K3_JOFF);
+          const float4 j = jr[__popc(mask & lt)];
+          const float u0 = wnn * j.x + Wt.x * j.y + Wt.y * j.z, u1 = Wt.x * j.x + Wt.z * j.y, u2 = Wt.y * j.x + Wt.w * j.z;
+#pragma unroll 1
+          for (unsigned bits = mask; bits; bits &= bits - 1) {
+            const float4 jk = *jr++;
+            hg[__ffs(bits) - 1] += u0 * jk.x + u1 * jk.y + u2 * jk.z;
+          }
+        }
+      }
+      float hrow[NVP];
+#pragma unroll
+      for (int k = 0; k < NVP; k++) { hrow[k] = mrow[k] + hg[k]; hg[k] = 0.f; }
+      const float dg = me ? dadd : 1.f, rhs0 = me ? -grad : 0.f;
+      const float dr = elim_solve2<0>(hrow, rhs0, dg);
+      if (me && !done) W_(L.o_dir + lane) = dr;
+      __syncwarp();
+      float alpha = 1.f;
+      int ls = 0;
+      bool exact = false;
+      float md = 0.f, mdabs = 0.f;  // (M dir)[lane] and the magnitude of its terms
+#pragma unroll
+      for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_dir + k); md += t; mdabs += fabsf(t); }
+      if (__any_sync(kAll, constrained && !done)) {
+        contact_pass3(L, L.o_dir, done ? 0 : ncon, ncw, 1);
+        __syncwarp();
+        const int nls = done ? 0 : ncon;
+        bool lsdone = done || !constrained;
+        bool flipped = false, lsconv = false;  // did a row change sides between 0 and alpha; did the search converge
+        float g, h;
+        bool fl;
+        ls_rows3(L, nls, ljar, dr, 1.f, &g, &h, &fl);
+        // the full Newton step crosses no row: it is the minimiser along the direction, no search needed
+        flipped = gballot(fl) != 0;
+        if (!flipped && !lsdone) { lsdone = true; lsconv = true; }
+        if (!__all_sync(kAll, lsdone)) {
+          const bool searched = !lsdone;
+          const float g0 = gsum16(me ? dr * (Ma - sm_) : 0.f), h0 = gsum16(me ? dr * md : 0.f);
+          float lo = 0.f, hi = -1.f;
+#pragma unroll 1
+          for (int k = 0; k < kTMaxLineSearch; k++) {
+            if (k > 0) ls_rows3(L, nls, ljar, dr, alpha, &g, &h, &fl);
+            g = gsum16(g) + g0 + alpha * h0;
+            h = gsum16(h) + h0;
+            if (!lsdone) {
+              if (fabsf(g) < MMZ_LS_TOL * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
+              else {
+                if (g < 0.f) lo = alpha; else hi = alpha;
+                float next = alpha - g / h;
+                if (hi >= 0.f && (next <= lo || next >= hi)) next = 0.5f * (lo + hi);
+                if (next <= lo && hi < 0.f) next = 2.f * alpha + 1e-6f;
+                if (next == alpha) lsdone = true;
+                else { alpha = next; ls++; }
+              }
+            }
+            if (__all_sync(kAll, lsdone)) break;
+          }
+          ls_rows3(L, nls, ljar, dr, alpha, &g, &h, &fl);  // sides at the accepted step against those at 0
+          const bool any = gballot(fl) != 0;
+          if (searched) flipped = any;
+        }
+        exact = !flipped && lsconv && fabsf(alpha - 1.f) < 1e-3f;
+        if (exact) alpha = 1.f;  // the minimiser of that quadratic is the Newton step itself
+      }
+      bool moved = false;
+      if (me && !done) {
+        const float st = alpha * dr;
+        moved = fabsf(st) > 2e-6f * fabsf(al) + 1e-6f;
+        al += st;
+        W_(L.o_qacc + lane) = al;
+        Ma += alpha * md;
+        Mabs += fabsf(alpha) * mdabs;  // triangle inequality: still an upper bound of the magnitude of the terms
+      }
+      if (lane == 0 && !done) {
+        IW(L.o_cnt + TN_ITER) = it + 1; IW(L.o_cnt + TN_ITER_SUM) += 1; IW(L.o_cnt + TN_LS_SUM) += ls;
+        if (it == kTMaxNewton - 1) IW(L.o_cnt + TN_CAPPED) += 1;
+      }
+      __syncwarp();
+      const unsigned movedbits = gballot(moved);
+      if (!constrained || movedbits == 0 || exact) done = true;
+      if (__all_sync(kAll, done)) break;
+    }
+    __syncwarp();
+  }
+
   // RK4 bookkeeping of stage i for this warp's two environments (solver view, lane = dof), right after their solve:
   // accumulate the stage (B weights), then move to the state of the next stage, or to the final combination after
   // stage 3 (classic tableau, A = 1/2, 1/2, 1). Positions integrate on the configuration manifold (mj_integratePos):
@@ -1532,17 +1803,18 @@ struct HEnv {
     {
       const int ncmax = __reduce_max_sync(kAll, I(L.o_cnt + TN_CON));
       for (int c = wid; c < ncmax; c += TW) {
-        if (V2) contact_rows2(L, c);
+        if (V2 || V3) contact_rows2(L, c);
         else contact_rows(L, c);
       }
     }
     // (solver v2 loads its registers first and has its own block barrier before it touches the Jacobian area: that one
     // also orders the contact rows above against their readers)
-    if (!V2) __syncthreads();
+    if (!V2 && !V3) __syncthreads();
     MMZ_TICK(5);
     // solver view: warp w owns environments w and w + 16
     limit_rows_g(L);
     if (V2) solve_g2(L, warmstart);
+    else if (V3) solve_g3(L, warmstart);
     else solve_g(L, warmstart);
     if (rk_stage >= 0) rk_update_g(L, rk_stage);  // in the shadow of the wait for the slowest solve of the block
 #ifdef MMZ_PHASE_TIMING

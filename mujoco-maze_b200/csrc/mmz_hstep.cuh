@@ -150,6 +150,13 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
     float4* nat = reinterpret_cast<float4*>(ws + L.o_nat * HS);
     T.jg = nat + T.genv * L.jes + (T.genv >> 4);
     T.fg = nat + L.fa_off + T.genv * (2 * L.maxcon);
+    T.hg = nullptr;
+    if (L.v3) {  // solver v3: one block per environment - Jacobian pool, (force, weights) pairs, Hessian rows of the 16 lanes
+      float4* base = nat + T.genv * L.es + (T.genv >> 4);
+      T.jg = base;
+      T.fg = base + L.njac;
+      T.hg = reinterpret_cast<float*>(base + L.njac + 2 * L.maxcon) + (T.e & 15) * (NVP + 1);
+    }
   }
   T.lane = T.e & 15;
   T.gshift = (T.e >> 4) * 16;
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
   const int e = T.e, wid = T.wid;
 #define S(i) ws[(i) * HS + e]
   // the mass matrix is only ever written on its (static) sparsity pattern: clear it once (solver v2 reads the pattern only)
-  if (BOX)
+  if (BOX && !HTask<NVP, BOX>::V3)
     for (int i = wid; i < L.nv * L.ldm; i += TW) S(L.o_M + i) = 0.f;
   for (int i = L.nv + wid; i < NVP; i += TW) { S(L.o_qacc + i) = 0.f; S(L.o_dir + i) = 0.f; }  // padding the solver reads
   // ---- state tile: every row is 32 consecutive environments = one 128-byte line per warp load
