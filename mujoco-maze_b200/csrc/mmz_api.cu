@@ -367,7 +367,7 @@ bool configure_h(mmz_env* h, int* rc) {
     }
     if (maxcon < 10) return false;  // does not fit: use the lanes-per-environment kernel
     L.maxcon = maxcon;
-  } else if (!getenv("MMZ_BOX_V1_LAYOUT")) {
+  } else {
     // Solver v3 (mmz_hkernel.cuh: solve_g3). In front: what stays live while the solver iterates. Then [A] the arrays the
     // solver view has loaded into registers by its block barrier, or that are dead by then (motion axes, mass matrix,
     // smooth forces, geom poses, body velocities, contact counts, rotation matrices): the natural-order area - per
@@ -388,7 +388,7 @@ bool configure_h(mmz_env* h, int* rc) {
     L.o_xmat = take(9 * L.nb);
     const int a_end = o;
     const int tail = 4 * L.nb + 10 * L.nb + 10 * L.nb + 6 * L.nb + 6 * L.nb + 6 * L.nb;  // xquat, iw, ic, acc, frc, fsub
-    const int static_smem = 256 + 16;  // mbarrier (+ the dummy scratch of the first solver)
+    const int static_smem = 256;  // mbarrier
     const int avail = (dev_smem - round_up(L.model_bytes, 128) - static_smem) / (HS * 4);  // slots per environment
     const int maxcon = std::min(32, 16 + 8 * nbox);  // two trips of 16 lanes
     const int hq = (16 * (nvp + 1) + 3) / 4;        // float4s of the 16 Hessian rows
@@ -409,29 +409,6 @@ bool configure_h(mmz_env* h, int* rc) {
     L.o_con = o;
     L.o_xquat = take(4 * L.nb); L.o_iw = take(10 * L.nb); L.o_ic = take(10 * L.nb);
     L.o_acc = take(6 * L.nb); L.o_frc = take(6 * L.nb); L.o_fsub = take(6 * L.nb);
-  } else {
-    L.o_gpos = take(3 * L.ng); L.o_gax = take(3 * L.ng); L.o_gmat = take(nbox > 0 ? 9 * nbox : 1);
-    L.o_cdof = take(6 * L.nv);
-    L.o_vel = take(6 * L.nb);
-    L.o_M = take(L.nv * L.ldm);
-    L.o_smooth = take(L.nv); L.o_dir = take(nvp);
-    L.o_gcnt = take(nitems); L.o_obs = take(L.obs_core);
-    // Last: the arrays that are dead once the mass matrix and the smooth forces exist (orientations, inertias, bias
-    // accelerations and forces). The contact slots are written after that point and OVERLAY them, then run on.
-    const int dead0 = o;
-    L.o_xquat = take(4 * L.nb); L.o_xmat = take(9 * L.nb); L.o_iw = take(10 * L.nb);
-    L.o_ic = take(10 * L.nb); L.o_acc = take(6 * L.nb); L.o_frc = take(6 * L.nb); L.o_fsub = take(6 * L.nb);
-    const int dead1 = o;
-    const int static_smem = 256 + TE * 16 * 16;  // mbarrier + the Jacobian scratch of the Hessian build
-    const int avail = (dev_smem - round_up(L.model_bytes, 128) - static_smem) / (HS * 4);  // slots per environment
-    if (avail < dead1) return false;
-    int maxcon = (avail - dead0) / L.cstride;
-    const int want = std::min(40, 16 + 8 * nbox);
-    if (maxcon > want) maxcon = want;
-    if (maxcon < 24) return false;  // does not fit: use the lanes-per-environment kernel
-    L.maxcon = maxcon;
-    L.o_con = dead0;
-    L.nslots = std::max(dead1, dead0 + maxcon * L.cstride);
   }
   h->TL = L;
   h->smem_bytes = round_up(L.model_bytes, 128) + L.nslots * HS * 4;

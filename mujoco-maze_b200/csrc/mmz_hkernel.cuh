@@ -144,22 +144,14 @@ enum { K_POS = 0, K_N = 3, K_T1 = 6, K_BODY1 = 9, K_BODY2 = 10, K_MPOS = 9, K_MN
        K3_JV = 4, K3_JOFF = 17, K3_STRIDE = 19 };  // solver v3: J dir per pyramid row (over the dead point / normal), offset of the contact's Jacobian entries
 static __device__ __noinline__ void write_contact_record2(float* c, const RawContact& rc, int b1, int b2, float iw, int g, int other);
 
-// one out-of-line copy of the record writer (it has several call sites); `c` points at element (slot 0, env) of the
-// contact block, consecutive fields are HS floats apart
-static __device__ __noinline__ void write_contact_record(float* c, const RawContact& rc, int b1, int b2, float iw, const float* par);
 
 template <int NVP, int BOX>
 struct HEnv {
   static constexpr bool V2 = BOX == 0;  // which solver (and contact record) the instance uses
-#ifdef MMZ_BOX_V1
-  static constexpr bool V3 = false;     // (development aid: the first solver for the box instances)
-#else
   static constexpr bool V3 = BOX != 0;  // box instances: the stored Jacobian on each contact's own dofs (solve_g3)
-#endif
   const mmz_model* m;
   const TDerived* dv;
   float* sm;
-  float4* jsc;              // [32 environments][16 dofs] scratch: contact Jacobian columns during the Hessian build (BOX)
   float4* jg;               // solver v2: this lane's environment in the Jacobian area, [contact][NVP + 1] float4
   float4* fg;               // solver v2: its per-contact (force, Hessian weights) pairs, [contact][2] float4
   float* hg;                // solver v3: this lane's row of the contact part of the Hessian, accumulated in shared memory
@@ -497,16 +489,10 @@ struct HEnv {
     if (b1 == b2 || m->body_parent[b1] == b2 || m->body_parent[b2] == b1) return false;
     return (m->geom_contype[g1] & m->geom_conaffinity[g2]) || (m->geom_contype[g2] & m->geom_conaffinity[g1]);
   }
-  // stores a narrow-phase record into contact slot `slot` (layout C_* of mmz_layout.h); the normal points
+  // stores a narrow-phase record into contact slot `slot` (layout K_* above); the normal points
   // from body b1 (geom1) to body b2 (geom2), -1 = world
   MMZ_DI void write_contact(const TLayout& L, int slot, const RawContact& rc, int b1, int b2, float iw, int g, int other) {
-    if (V2 || V3) {
-      write_contact_record2(sm + (L.o_con + slot * L.cstride) * HS + e, rc, b1, b2, iw, g, other);
-    } else {
-      float par[9];
-      mix_params(g, other, par);
-      write_contact_record(sm + (L.o_con + slot * L.cstride) * HS + e, rc, b1, b2, iw, par);
-    }
+    write_contact_record2(sm + (L.o_con + slot * L.cstride) * HS + e, rc, b1, b2, iw, g, other);
   }
   // number of collision items: one per geom, then (BOX only) BCAND candidate slots per box geom
   static constexpr int BCELLS = 9;                       // maze cells a box geom can reach (3 x 3)
@@ -779,49 +765,6 @@ struct HEnv {
     S(o + K_AREF + 2) = -bb * (jv0 + mu * jv2) - kr;
     S(o + K_AREF + 3) = -bb * (jv0 - mu * jv2) - kr;
   }
-  MMZ_DI void contact_rows(const TLayout& L, int c) {
-    if (c >= I(L.o_cnt + TN_CON)) return;
-    const int o = L.o_con + c * L.cstride;
-    float rf[3], cp[3], fr[9], solref[2], solimp[5], v[3] = {0.f, 0.f, 0.f};
-    ref(L, rf);
-#pragma unroll
-    for (int k = 0; k < 3; k++) cp[k] = S(o + C_POS + k) - rf[k];
-#pragma unroll
-    for (int k = 0; k < 9; k++) fr[k] = S(o + C_FRAME + k);
-    const float dist = S(o + C_DIST), margin = S(o + C_MARGIN), invw = S(o + C_INVW), mu = S(o + C_MU);
-#pragma unroll
-    for (int k = 0; k < 2; k++) solref[k] = S(o + C_SOLREF + k);
-#pragma unroll
-    for (int k = 0; k < 5; k++) solimp[k] = S(o + C_SOLIMP + k);
-    const int b1 = __float_as_int(S(o + C_BODY1)), b2 = __float_as_int(S(o + C_BODY2));
-    const int mask1 = b1 >= 0 ? m->body_dofmask[b1] : 0, mask2 = b2 >= 0 ? m->body_dofmask[b2] : 0;
-#pragma unroll 1
-    for (int side = 0; side < 2; side++) {
-      const int b = side == 0 ? b2 : b1;
-      if (b < 0) continue;
-      float bv[6], wxp[3];
-#pragma unroll
-      for (int k = 0; k < 6; k++) bv[k] = S(L.o_vel + 6 * b + k);
-      cross3(wxp, bv, cp);
-      const float sg = side == 0 ? 1.f : -1.f;
-#pragma unroll
-      for (int k = 0; k < 3; k++) v[k] += sg * (bv[3 + k] + wxp[k]);
-    }
-    const float jv0 = dot3(fr, v), jv1 = dot3(fr + 3, v), jv2 = dot3(fr + 6, v);
-    float D, kr, bb;
-    row_params(solref, solimp, dist, margin, invw * (1.f + mu * mu), &D, &kr, &bb);
-#pragma unroll
-    for (int k = 0; k < 3; k++) S(o + C_POS + k) = cp[k];
-    S(o + C_MPOS) = __int_as_float(mask2 & ~mask1);
-    S(o + C_MNEG) = __int_as_float(mask1 & ~mask2);
-    // all edges of the pyramid share R = 2 mu^2 R_first
-    S(o + C_D) = 1.f / fmaxf(kMinVal, 2.f * mu * mu / D);
-    S(o + C_AREF + 0) = -bb * (jv0 + mu * jv1) - kr;
-    S(o + C_AREF + 1) = -bb * (jv0 - mu * jv1) - kr;
-    S(o + C_AREF + 2) = -bb * (jv0 + mu * jv2) - kr;
-    S(o + C_AREF + 3) = -bb * (jv0 - mu * jv2) - kr;
-  }
-
   // named barriers among a subset of the block's warps (ids 1..15; 0 is __syncthreads)
   MMZ_DI static void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
   MMZ_DI static void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -861,28 +804,6 @@ struct HEnv {
     limD[0] = me ? W_(L.o_lim + 4 * lane) : 0.f; limD[1] = me ? W_(L.o_lim + 4 * lane + 1) : 0.f;
     limA[0] = me ? W_(L.o_lim + 4 * lane + 2) : 0.f; limA[1] = me ? W_(L.o_lim + 4 * lane + 3) : 0.f;
   }
-  // Lane i holds row i of the symmetric positive-definite H (NVP registers) and element i of the right-hand
-  // side. Gauss-Jordan without pivoting: step j clears column j in EVERY other row (the rows above the pivot cost
-  // nothing extra in a SIMD step, and there is no back substitution), the pivot row is broadcast by shuffles, and
-  // each lane keeps the reciprocal of its own pivot for the final scaling. Rows / columns beyond the model's nv
-  // are the identity with a zero right-hand side (the caller pads them): their multipliers are exactly zero.
-  MMZ_DI float elim_solve(float (&h)[NVP], float rhs) const {
-    float invd = 1.f;
-#pragma unroll
-    for (int j = 0; j < NVP; j++) {
-      const float piv = fmaxf(__shfl_sync(kAll, h[j], j, 16), kMinVal);
-      float inv;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv));  // 1 ulp: as good as the approximate division of the build
-      const float rj = __shfl_sync(kAll, rhs, j, 16);
-      const bool own = lane == j;
-      const float f = own ? 0.f : h[j] * inv;
-      invd = own ? inv : invd;
-      rhs -= f * rj;
-#pragma unroll
-      for (int k = j + 1; k < NVP; k++) h[k] -= f * __shfl_sync(kAll, h[k], j, 16);
-    }
-    return rhs * invd;
-  }
   // The same elimination for solver v2. `dg` is added to this lane's diagonal element on the fly (the joint-limit rows;
   // 1 for the identity rows beyond the model), so the caller's row is a plain copy of the mass-matrix row. TOPO 1 =
   // the Ant's tree (a free root, dofs 0-5, and 2-dof chains (6,7), (8,9), ... hanging off it): the pivots run from the
@@ -916,212 +837,6 @@ struct HEnv {
     }
     return rhs * invd;
   }
-  // this lane's column of the contact-frame Jacobian of the contact block at slot offset cs
-  MMZ_DI void contact_jac(int cs, const float (&cd)[6], float* jn, float* jt1, float* jt2) const {
-    const int mp = __float_as_int(W_(cs + C_MPOS)), mn = __float_as_int(W_(cs + C_MNEG));
-    const float s = (float)(mp >> lane & 1) - (float)(mn >> lane & 1);
-    float p[3], fr[9], wxp[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) p[k] = W_(cs + C_POS + k);
-#pragma unroll
-    for (int k = 0; k < 9; k++) fr[k] = W_(cs + C_FRAME + k);
-    cross3(wxp, cd, p);
-    const float v[3] = {s * (cd[3] + wxp[0]), s * (cd[4] + wxp[1]), s * (cd[5] + wxp[2])};
-    *jn = dot3(fr, v); *jt1 = dot3(fr + 3, v); *jt2 = dot3(fr + 6, v);
-  }
-  MMZ_DI void contact_products(const TLayout& L, const float (&cd)[6], float x, int ncon, int ncw, int which, float* grad,
-                               float* mag) {
-#pragma unroll 1
-    for (int c = 0; c < ncw; c++) {
-      const int cs = L.o_con + c * L.cstride;
-      const bool valid = c < ncon;
-      float jn, jt1, jt2;
-      contact_jac(cs, cd, &jn, &jt1, &jt2);
-      if (!valid) { jn = 0.f; jt1 = 0.f; jt2 = 0.f; }
-      const float mu = valid ? W_(cs + C_MU) : 0.f;
-      float s0 = jn * x, s1 = jt1 * x, s2 = jt2 * x, sa = (fabsf(jn) + mu * (fabsf(jt1) + fabsf(jt2))) * fabsf(x);
-#pragma unroll
-      for (int off = 8; off > 0; off >>= 1) {
-        s0 += __shfl_xor_sync(kAll, s0, off);
-        s1 += __shfl_xor_sync(kAll, s1, off);
-        s2 += __shfl_xor_sync(kAll, s2, off);
-        if (which == 0) sa += __shfl_xor_sync(kAll, sa, off);
-      }
-      if (!valid) continue;  // no shuffles below
-      const float e0 = s0 + mu * s1, e1 = s0 - mu * s1, e2 = s0 + mu * s2, e3 = s0 - mu * s2;
-      if (which == 0) {
-        const float r0 = W_(cs + C_AREF), r1 = W_(cs + C_AREF + 1), r2 = W_(cs + C_AREF + 2), r3 = W_(cs + C_AREF + 3);
-        const float j0 = e0 - r0, j1 = e1 - r1, j2 = e2 - r2, j3 = e3 - r3;
-        if (lane == 0) { W_(cs + C_JAR) = j0; W_(cs + C_JAR + 1) = j1; W_(cs + C_JAR + 2) = j2; W_(cs + C_JAR + 3) = j3; }
-        const float a0 = j0 < 0.f, a1 = j1 < 0.f, a2 = j2 < 0.f, a3 = j3 < 0.f;
-        const float D = W_(cs + C_D);
-        const float f0 = a0 * D * j0, f1 = a1 * D * j1, f2 = a2 * D * j2, f3 = a3 * D * j3;
-        *grad += jn * (f0 + f1 + f2 + f3) + jt1 * (mu * (f0 - f1)) + jt2 * (mu * (f2 - f3));
-        const float bound = sa + fmaxf(fmaxf(fabsf(r0), fabsf(r1)), fmaxf(fabsf(r2), fabsf(r3)));
-        *mag += D * bound * ((a0 + a1 + a2 + a3) * fabsf(jn) + mu * ((a0 + a1) * fabsf(jt1) + (a2 + a3) * fabsf(jt2)));
-      } else if (lane == 0) {
-        W_(cs + C_JV) = e0; W_(cs + C_JV + 1) = e1; W_(cs + C_JV + 2) = e2; W_(cs + C_JV + 3) = e3;
-      }
-    }
-  }
-  // Newton solver (mj_solNewton), lanes <-> dofs; same algorithm as mmz_dyn.cuh: Env::solve
-  MMZ_DI void solve_g(const TLayout& L, bool warmstart) {
-    const int nv = L.nv, ncon = IW(L.o_cnt + TN_CON);
-    int ncw = max(ncon, __shfl_xor_sync(kAll, ncon, 16));  // the two environments of the warp
-    const bool me = lane < nv;
-    const unsigned limbits = gballot(limD[0] > 0.f || limD[1] > 0.f);
-    const bool constrained = ncon > 0 || limbits != 0;
-    float cd[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) cd[k] = me ? W_(L.o_cdof + 6 * lane + k) : 0.f;
-    float mrow[NVP];  // this lane's row of the mass matrix (zero outside the model)
-#pragma unroll
-    for (int k = 0; k < NVP; k++) mrow[k] = (me && k < nv) ? W_(L.o_M + lane * L.ldm + k) : 0.f;
-    const float sm_ = me ? W_(L.o_smooth + lane) : 0.f;
-    float al = (warmstart && me) ? W_(L.o_qacc + lane) : 0.f;
-    if (!(fabsf(al) < kMaxVal)) al = 0.f;  // a blown-up environment restarts from zero
-    if (me) W_(L.o_qacc + lane) = al;
-    const int nlim = __popc(gballot(limD[0] > 0.f)) + __popc(gballot(limD[1] > 0.f));
-    if (lane == 0) {
-      IW(L.o_cnt + TN_ITER) = 0; IW(L.o_cnt + TN_LIM) = nlim;
-      IW(L.o_cnt + TN_CON_MAX) = max(IW(L.o_cnt + TN_CON_MAX), ncon);
-    }
-    __syncwarp();
-    bool done = false;
-    // (M qacc)[lane] and the magnitude of its terms: from scratch at the warm start, then updated with every step
-    float Ma = 0.f, Mabs = 0.f;
-#pragma unroll
-    for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_qacc + k); Ma += t; Mabs += fabsf(t); }  // padded to NVP
-#pragma unroll 1
-    for (int it = 0; it < kTMaxNewton; it++) {
-      float grad = Ma - sm_, dadd = 0.f;
-      float mag = Mabs + fabsf(sm_);
-      float ljar[2];
-#pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const float sign = s == 0 ? 1.f : -1.f;
-        ljar[s] = sign * al - limA[s];
-        if (limD[s] > 0.f && ljar[s] < 0.f) {
-          grad += limD[s] * ljar[s] * sign;
-          mag += limD[s] * (fabsf(al) + fabsf(limA[s]));
-          dadd += limD[s];
-        }
-      }
-      contact_products(L, cd, al, ncon, ncw, 0, &grad, &mag);
-      if (gballot(fabsf(grad) > tol * mag + 1e-30f) == 0) done = true;
-      if (__all_sync(kAll, done)) break;
-      __syncwarp();
-      float hrow[NVP];
-#pragma unroll
-      for (int k = 0; k < NVP; k++) {
-        const float mk = mrow[k];
-        hrow[k] = (k == lane) ? (me ? mk + dadd : 1.f) : mk;
-      }
-#pragma unroll 1
-      for (int c = 0; c < ncw; c++) {
-        const int cs = L.o_con + c * L.cstride;
-        const bool valid = c < ncon;
-        const float a0 = valid && W_(cs + C_JAR) < 0.f, a1 = valid && W_(cs + C_JAR + 1) < 0.f, a2 = valid && W_(cs + C_JAR + 2) < 0.f,
-                    a3 = valid && W_(cs + C_JAR + 3) < 0.f;
-        const bool act = a0 + a1 + a2 + a3 != 0.f;
-        if (!__any_sync(kAll, act)) continue;
-        float jn, jt1, jt2;
-        contact_jac(cs, cd, &jn, &jt1, &jt2);
-        if (!act) { jn = 0.f; jt1 = 0.f; jt2 = 0.f; }
-        const float D = act ? W_(cs + C_D) : 0.f, mu = act ? W_(cs + C_MU) : 0.f;
-        const float wnn = D * (a0 + a1 + a2 + a3), wn1 = D * mu * (a0 - a1), wn2 = D * mu * (a2 - a3);
-        const float w11 = D * mu * mu * (a0 + a1), w22 = D * mu * mu * (a2 + a3);
-        const float u0 = wnn * jn + wn1 * jt1 + wn2 * jt2, u1 = wn1 * jn + w11 * jt1, u2 = wn2 * jn + w22 * jt2;
-        // every lane needs the Jacobian columns of all dofs: through a 16-byte scratch entry per (environment, dof),
-        // one vector load per dof instead of three shuffles
-        __syncwarp();
-        jsc[genv * 16 + lane] = make_float4(jn, jt1, jt2, 0.f);
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < NVP; k++) {
-          const float4 jk = jsc[genv * 16 + k];
-          hrow[k] += u0 * jk.x + u1 * jk.y + u2 * jk.z;
-        }
-      }
-      const float dr = elim_solve(hrow, me ? -grad : 0.f);
-      if (me && !done) W_(L.o_dir + lane) = dr;
-      __syncwarp();
-      float alpha = 1.f;
-      int ls = 0;
-      bool exact = false;
-      float md = 0.f, mdabs = 0.f;  // (M dir)[lane] and the magnitude of its terms
-#pragma unroll
-      for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_dir + k); md += t; mdabs += fabsf(t); }
-      if (__any_sync(kAll, constrained && !done)) {
-        float dummy0 = 0.f, dummy1 = 0.f;
-        contact_products(L, cd, dr, done ? 0 : ncon, ncw, 1, &dummy0, &dummy1);
-        __syncwarp();
-        const float g0 = gsum16(me ? dr * (Ma - sm_) : 0.f), h0 = gsum16(me ? dr * md : 0.f);
-        float lo = 0.f, hi = -1.f;
-        bool lsdone = done || !constrained;
-        bool flipped = true, lsconv = false;  // did a row change sides between 0 and alpha; did the search converge
-#pragma unroll 1
-        for (int k = 0; k < kTMaxLineSearch; k++) {
-          float g = 0.f, h = 0.f;
-          bool fl = false;
-#pragma unroll
-          for (int s = 0; s < 2; s++) {
-            const float jv = s == 0 ? dr : -dr, x = ljar[s] + alpha * jv;
-            if (limD[s] > 0.f && x < 0.f) { g += limD[s] * x * jv; h += limD[s] * jv * jv; }
-            fl |= limD[s] > 0.f && (x < 0.f) != (ljar[s] < 0.f);
-          }
-          if (!lsdone) {
-#pragma unroll 1
-            for (int r = lane; r < 4 * ncon; r += 16) {
-              const int cs = L.o_con + (r >> 2) * L.cstride;
-              const float jv = W_(cs + C_JV + (r & 3)), jar = W_(cs + C_JAR + (r & 3)), x = jar + alpha * jv, D = W_(cs + C_D);
-              if (x < 0.f) { g += D * x * jv; h += D * jv * jv; }
-              fl |= (x < 0.f) != (jar < 0.f);
-            }
-            flipped = fl;
-          }
-          g = gsum16(g) + g0 + alpha * h0;
-          h = gsum16(h) + h0;
-          if (!lsdone) {
-            if (fabsf(g) < MMZ_LS_TOL * fmaxf(1e-6f, fabsf(g0))) { lsdone = true; lsconv = true; }
-            else {
-              if (g < 0.f) lo = alpha; else hi = alpha;
-              float next = alpha - g / h;
-              if (hi >= 0.f && (next <= lo || next >= hi)) next = 0.5f * (lo + hi);
-              if (next <= lo && hi < 0.f) next = 2.f * alpha + 1e-6f;
-              if (next == alpha) lsdone = true;
-              else { alpha = next; ls++; }
-            }
-          }
-          if (__all_sync(kAll, lsdone)) break;
-        }
-        // No row of this environment changed sides on [0, alpha] (rows are linear in alpha) and alpha minimises the
-        // cost along the Newton direction of exactly that active set: the new point is the solution, and the
-        // gradient pass that would confirm it is skipped.
-        exact = gballot(flipped) == 0 && lsconv && fabsf(alpha - 1.f) < 1e-3f;
-        if (exact) alpha = 1.f;  // the minimiser of that quadratic is the Newton step itself
-      }
-      bool moved = false;
-      if (me && !done) {
-        const float st = alpha * dr;
-        moved = fabsf(st) > 2e-6f * fabsf(al) + 1e-6f;
-        al += st;
-        W_(L.o_qacc + lane) = al;
-        Ma += alpha * md;
-        Mabs += fabsf(alpha) * mdabs;  // triangle inequality: still an upper bound of the magnitude of the terms
-      }
-      if (lane == 0 && !done) {
-        IW(L.o_cnt + TN_ITER) = it + 1; IW(L.o_cnt + TN_ITER_SUM) += 1; IW(L.o_cnt + TN_LS_SUM) += ls;
-        if (it == kTMaxNewton - 1) IW(L.o_cnt + TN_CAPPED) += 1;
-      }
-      __syncwarp();
-      const unsigned movedbits = gballot(moved);
-      if (!constrained || movedbits == 0 || exact) done = true;
-      if (__all_sync(kAll, done)) break;
-    }
-    __syncwarp();
-  }
-
   // ================================================================== solver v2 (models without box geoms)
   // The contact Jacobian is built ONCE per forward evaluation and kept in shared memory, one float4 per (contact, dof):
   // (J_n, mu J_t1, mu J_t2, |J_n| + mu (|J_t1| + |J_t2|)). With the friction coefficient folded into the tangential
@@ -1803,19 +1518,16 @@ struct HEnv {
     {
       const int ncmax = __reduce_max_sync(kAll, I(L.o_cnt + TN_CON));
       for (int c = wid; c < ncmax; c += TW) {
-        if (V2 || V3) contact_rows2(L, c);
-        else contact_rows(L, c);
+        contact_rows2(L, c);
       }
     }
     // (solver v2 loads its registers first and has its own block barrier before it touches the Jacobian area: that one
     // also orders the contact rows above against their readers)
-    if (!V2 && !V3) __syncthreads();
     MMZ_TICK(5);
     // solver view: warp w owns environments w and w + 16
     limit_rows_g(L);
     if (V2) solve_g2(L, warmstart);
-    else if (V3) solve_g3(L, warmstart);
-    else solve_g(L, warmstart);
+    else solve_g3(L, warmstart);
     if (rk_stage >= 0) rk_update_g(L, rk_stage);  // in the shadow of the wait for the slowest solve of the block
 #ifdef MMZ_PHASE_TIMING
     const long long ts1_ = clock64();
@@ -1865,25 +1577,6 @@ struct HEnv {
 #undef S
 #undef W_
 };
-
-static __device__ __noinline__ void write_contact_record(float* c, const RawContact& rc, int b1, int b2, float iw, const float* par) {
-  float fr[9];
-#pragma unroll
-  for (int k = 0; k < 3; k++) { fr[k] = rc.normal[k]; fr[3 + k] = rc.hint[k]; }
-  make_frame(fr);
-#pragma unroll
-  for (int k = 0; k < 3; k++) c[(C_POS + k) * HS] = rc.pos[k];
-#pragma unroll
-  for (int k = 0; k < 9; k++) c[(C_FRAME + k) * HS] = fr[k];
-  c[C_DIST * HS] = rc.dist;
-  c[C_MARGIN * HS] = par[0];
-  c[C_MU * HS] = par[1];
-#pragma unroll
-  for (int k = 0; k < 7; k++) c[(C_SOLREF + k) * HS] = par[2 + k];
-  c[C_INVW * HS] = iw;
-  c[C_BODY1 * HS] = __int_as_float(b1);
-  c[C_BODY2 * HS] = __int_as_float(b2);
-}
 
 static __device__ __noinline__ void write_contact_record2(float* c, const RawContact& rc, int b1, int b2, float iw, int g, int other) {
   float fr[9];

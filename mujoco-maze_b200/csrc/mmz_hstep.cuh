@@ -110,7 +110,6 @@ template <int NVP, int BOX, int MODE>
 __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant__ TArgs A) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;
-  __shared__ float4 jscratch[BOX ? TE * 16 : 1];  // the Hessian build of the first solver (models with box geoms)
   const TLayout& L = A.L;
   const int tid = threadIdx.x;
   const int env0 = (A.block0 + blockIdx.x) * TE;
@@ -139,7 +138,6 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
   T.m = reinterpret_cast<const mmz_model*>(smem);
   T.dv = reinterpret_cast<const TDerived*>(smem + ((sizeof(mmz_model) + 15) & ~15));
   T.sm = ws;
-  T.jsc = jscratch;
   T.e = tid % 32;
   T.wid = tid / 32;
   T.genv = T.wid + 16 * (T.e >> 4);
@@ -163,9 +161,6 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
   T.tol = A.tol;
   const int e = T.e, wid = T.wid;
 #define S(i) ws[(i) * HS + e]
-  // the mass matrix is only ever written on its (static) sparsity pattern: clear it once (solver v2 reads the pattern only)
-  if (BOX && !HTask<NVP, BOX>::V3)
-    for (int i = wid; i < L.nv * L.ldm; i += TW) S(L.o_M + i) = 0.f;
   for (int i = L.nv + wid; i < NVP; i += TW) { S(L.o_qacc + i) = 0.f; S(L.o_dir + i) = 0.f; }  // padding the solver reads
   // ---- state tile: every row is 32 consecutive environments = one 128-byte line per warp load
   if (MODE != TMODE_RESET || A.mask != nullptr) {
