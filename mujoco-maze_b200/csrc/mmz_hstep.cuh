@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
     T.jg = nat + T.genv * L.jes + (T.genv >> 4);
     T.fg = nat + L.fa_off + T.genv * (2 * L.maxcon);
     T.hg = nullptr;
-    if (L.v3) {  // solver v3: one block per environment - Jacobian pool, (force, weights) pairs, Hessian rows of the 16 lanes
+    if (BOX && L.v3) {  // solver v3: one block per environment - Jacobian pool, (force, weights) pairs, Hessian rows of the 16 lanes
       float4* base = nat + T.genv * L.es + (T.genv >> 4);
       T.jg = base;
       T.fg = base + L.njac;
