@@ -394,18 +394,21 @@ def main():
         sim.set_obs_peers([], 0)
 
     # ---- end to end through the C-ABI host call: pinned host buffers, copies inside the timed region
-    h_acts = [a.cpu().pin_memory() for a in acts[:4]]
+    # (the same episode phase and the same actions as the device-resident loop above: the environments are reset again,
+    # the warm-up steps go through the host call too)
+    h_acts = [a.cpu().pin_memory() for a in acts]
     h_obs = torch.empty((n_envs, od), dtype=torch.float32).pin_memory()
     h_rew = torch.empty((n_envs,), dtype=torch.float32).pin_memory()
     h_done = torch.empty((n_envs,), dtype=torch.uint8).pin_memory()
     h_info = torch.empty((n_envs, 4), dtype=torch.float32).pin_memory()
-    e2e_steps = max(5, args.steps // 2)
-    for i in range(3):
-        sim.step_host(h_acts[i % 4], h_obs, h_rew, h_done, h_info)
+    e2e_steps = args.steps
+    sim.reset(seed=0)
+    for i in range(args.warmup):
+        sim.step_host(h_acts[i % len(h_acts)], h_obs, h_rew, h_done, h_info)
     barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        sim.step_host(h_acts[i % 4], h_obs, h_rew, h_done, h_info)
+    for i in range(args.warmup, args.warmup + e2e_steps):
+        sim.step_host(h_acts[i % len(h_acts)], h_obs, h_rew, h_done, h_info)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -457,7 +460,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": world * n_envs * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": n_envs * nu * 4, "d2h_bytes_per_step": n_envs * (od * 4 + 4 + 1 + 16),
-                    "steps": e2e_steps, "api": "mmz_step_host (C ABI, pinned host buffers, synchronous)"},
+                    "steps": e2e_steps, "api": "mmz_step_host (C ABI, synchronous; pinned host buffers mapped into the device address space: one launch, the blocks read the actions and write the results over PCIe as they finish)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,

@@ -116,12 +116,16 @@ int mmz_step(mmz_handle h, const float* d_action, float* d_obs, float* d_reward,
 int mmz_step_k(mmz_handle h, int K, const float* d_actions, float* d_obs, float* d_reward, uint8_t* d_done, float* d_info,
                void* stream);
 
-/* Same step through HOST buffers: H2D of the actions, the kernel, D2H of
- * obs/reward/done/info, then a stream synchronise. This is the end-to-end
- * call a host-resident caller (the reference's numpy world) makes. Batches of
- * 64 blocks or more run as 4 block ranges on internal streams so that the
- * copies of one range overlap the kernel of another; results are identical
- * to mmz_step (environments are independent). */
+/* Same step through HOST buffers, then a stream synchronise. This is the
+ * end-to-end call a host-resident caller (the reference's numpy world) makes.
+ * PINNED buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are
+ * mapped into the device's address space: the step kernel reads the actions
+ * and writes obs/reward/done/info straight over PCIe, block by block, under
+ * the physics of the blocks still running - one launch, no staging copies.
+ * Pageable buffers (or MMZ_HOST_ZERO_COPY=0) take the staged path: H2D of the
+ * actions, the kernel, D2H of the results, batches of 64 blocks or more as 4
+ * block ranges on internal streams so that the copies of one range overlap the
+ * kernel of another. Results are identical to mmz_step either way. */
 int mmz_step_host(mmz_handle h, const float* h_action, float* h_obs, float* h_reward, uint8_t* h_done, float* h_info,
                   void* stream);
 

@@ -838,6 +838,29 @@ int mmz_step_host(mmz_handle h, const float* h_action, float* h_obs, float* h_re
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = h->n;
+  {
+    // Pinned (page-locked) host buffers are mapped into the device's address space (unified addressing): the step kernel
+    // reads the actions and writes observations / reward / done / info straight over PCIe - each block as it finishes,
+    // under the physics of the blocks still running. No staging copies, no launch split: ONE launch, then the
+    // synchronisation the host contract asks for. Pageable buffers (or MMZ_HOST_ZERO_COPY=0) take the staged path below.
+    const char* zc = getenv("MMZ_HOST_ZERO_COPY");
+    const bool zero_copy = !(zc && zc[0] == '0');
+    auto mapped = [](const void* p, void** out) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+      if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return false;
+      *out = at.devicePointer;
+      return true;
+    };
+    void *da = nullptr, *dob = nullptr, *dr = nullptr, *dd = nullptr, *di = nullptr;
+    if (zero_copy && mapped(h_action, &da) && mapped(h_obs, &dob) && mapped(h_reward, &dr) && mapped(h_done, &dd) &&
+        (!h_info || mapped(h_info, &di))) {
+      int rc = mmz_step(h, (const float*)da, (float*)dob, (float*)dr, (uint8_t*)dd, (float*)di, stream);
+      if (rc != MMZ_OK) return rc;
+      CUDA_TRY(cudaStreamSynchronize(s));
+      return MMZ_OK;
+    }
+  }
   if (!h->d_done) {  // d_done is allocated last: a staging set that failed half-way is rebuilt
     cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_info);
     h->d_action = h->d_obs = h->d_reward = h->d_info = nullptr;

@@ -130,8 +130,11 @@ __device__ unsigned long long g_phase[16];
 __device__ unsigned g_iter_hist[16];
 __device__ unsigned long long g_wsolve[16], g_wwait[16];  // per warp of block 0: its own solve, its wait for the slowest
 #define MMZ_TICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_phase[i] += t_ - tick_; tick_ = t_; } } while (0)
+__device__ unsigned long long g_sec[16];  // solver sections, summed over the warps of block 0 (slot 15: Newton iterations)
+#define MMZ_STICK(i) do { if (blockIdx.x == 0 && e == 0) { const long long t_ = clock64(); atomicAdd(&g_sec[i], (unsigned long long)(t_ - stick_)); stick_ = t_; } } while (0)
 #else
 #define MMZ_TICK(i) do { } while (0)
+#define MMZ_STICK(i) do { } while (0)
 #endif
 
 // Contact record of solver v2 (floats; mmz_layout.h C_* is the record of the first solver). The narrow phase leaves
@@ -812,16 +815,55 @@ struct HEnv {
   template <int TOPO>
   MMZ_DI float elim_solve2(float (&h)[NVP], float rhs, float dg) const {
     float invd = 1.f;
+    if (TOPO == 1 && NVP == 14) {
+      // The four ankle rows do not couple with each other, and once they are gone neither do the four hip rows: their
+      // pivots run SIDE BY SIDE (a lane that is one of the four pivots has a zero multiplier for the other three, so the
+      // rows the shuffles read are the ones a one-by-one elimination would read). The chain of dependent (shuffle,
+      // reciprocal, multiply-add) steps is 1 + 1 + 6 long instead of 14.
 #pragma unroll
-    for (int jj = 0; jj < NVP; jj++) {
+      for (int ph = 0; ph < 2; ph++) {
+        float f[4], t[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const int j = 7 + 2 * m - ph;
+          const bool own = lane == j;
+          float hd = h[j];
+          asm("" : "+f"(hd));  // opaque: four selects on (lane == j) over one array otherwise become h[lane] in LOCAL memory
+          const float hj = own ? hd + dg : hd;
+          const float piv = fmaxf(__shfl_sync(kAll, hj, j, 16), kMinVal);
+          float inv;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv));
+          f[m] = own ? 0.f : hd * inv;
+          invd = own ? inv : invd;
+          t[m] = __shfl_sync(kAll, rhs, j, 16);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; m++) rhs -= f[m] * t[m];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+#pragma unroll
+          for (int m = 0; m < 4; m++) t[m] = __shfl_sync(kAll, h[k], 7 + 2 * m - ph, 16);
+#pragma unroll
+          for (int m = 0; m < 4; m++) h[k] -= f[m] * t[m];
+        }
+        if (ph == 0) {
+#pragma unroll
+          for (int m = 0; m < 4; m++) h[6 + 2 * m] -= f[m] * __shfl_sync(kAll, h[6 + 2 * m], 7 + 2 * m, 16);
+        }
+      }
+    }
+#pragma unroll
+    for (int jj = (TOPO == 1 && NVP == 14) ? 8 : 0; jj < NVP; jj++) {
       const int j = TOPO == 1 ? NVP - 1 - jj : jj;
       const bool own = lane == j;
-      const float hj = own ? h[j] + dg : h[j];
+      float hd = h[j];
+      asm("" : "+f"(hd));
+      const float hj = own ? hd + dg : hd;
       const float piv = fmaxf(__shfl_sync(kAll, hj, j, 16), kMinVal);
       float inv;
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(piv));
       const float rj = __shfl_sync(kAll, rhs, j, 16);
-      const float f = own ? 0.f : h[j] * inv;
+      const float f = own ? 0.f : hd * inv;
       invd = own ? inv : invd;
       rhs -= f * rj;
       if (TOPO == 1) {
@@ -898,6 +940,9 @@ struct HEnv {
   // Newton solver (mj_solNewton), same algorithm and stopping rules as solve_g
   MMZ_DI void solve_g2(const TLayout& L, bool warmstart) {
     const int nv = L.nv, ncon = IW(L.o_cnt + TN_CON);
+#ifdef MMZ_PHASE_TIMING
+    long long stick_ = clock64();
+#endif
     const int ncw = max(ncon, __shfl_xor_sync(kAll, ncon, 16));  // the two environments of the warp
     const bool me = lane < nv;
     const unsigned limbits = gballot(limD[0] > 0.f || limD[1] > 0.f);
@@ -930,6 +975,7 @@ struct HEnv {
 #pragma unroll
     for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_qacc + k); Ma += t; Mabs += fabsf(t); }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    MMZ_STICK(0);  // prologue: register loads, block barrier, Jacobian
 #pragma unroll 1
     for (int it = 0; it < kTMaxNewton; it++) {
       float grad = Ma - sm_, dadd = 0.f;
@@ -947,35 +993,47 @@ struct HEnv {
       }
       contact_pass_grad(L, ncon, ncw);
       __syncwarp();
+      MMZ_STICK(1);  // contact pass (lane = contact)
 #pragma unroll 1
-      for (int c = 0; c < ncw; c++) {
+      for (int c = 0; c < ncw; c += 2) {  // two contacts per trip: four loads in flight (same order of additions as one by one)
+        const bool two = c + 1 < ncw;
         const float4 j = lane < NVP ? jrow(c)[lane] : zero4, F = fg[2 * c];
+        const float4 j1 = (two && lane < NVP) ? jrow(c + 1)[lane] : zero4, F1 = two ? fg[2 * c + 2] : zero4;
         grad += j.x * F.x + j.y * F.y + j.z * F.z;
         mag = fmaf(j.w, F.w, mag);
+        grad += j1.x * F1.x + j1.y * F1.y + j1.z * F1.z;
+        mag = fmaf(j1.w, F1.w, mag);
       }
       if (gballot(me && fabsf(grad) > tol * mag + 1e-30f) == 0) done = true;
+      MMZ_STICK(2);  // gradient (lane = dof)
       if (__all_sync(kAll, done)) break;
       float hrow[NVP];
 #pragma unroll
       for (int k = 0; k < NVP; k++) hrow[k] = mrow[k];  // the diagonal terms of the limit rows join in the elimination
 #pragma unroll 1
-      for (int c = 0; c < ncw; c++) {
-        const float4 Wt = fg[2 * c + 1];
-        const float wnn = Wt.z + Wt.w;
-        if (!__any_sync(kAll, wnn != 0.f)) continue;  // no active row in this contact, in either environment
-        const float4 j = lane < NVP ? jrow(c)[lane] : zero4;
+      for (int c = 0; c < ncw; c += 2) {  // two contacts per trip (loads of both in flight; same order of additions as one by one)
+        const bool two = c + 1 < ncw;
+        const float4 Wt = fg[2 * c + 1], Wb = two ? fg[2 * c + 3] : zero4;
+        const float wnn = Wt.z + Wt.w, wnb = Wb.z + Wb.w;
+        if (!__any_sync(kAll, wnn != 0.f || wnb != 0.f)) continue;  // no active row in these contacts, in either environment
+        const float4 j = lane < NVP ? jrow(c)[lane] : zero4, jb = (two && lane < NVP) ? jrow(c + 1)[lane] : zero4;
         const float u0 = wnn * j.x + Wt.x * j.y + Wt.y * j.z, u1 = Wt.x * j.x + Wt.z * j.y, u2 = Wt.y * j.x + Wt.w * j.z;
+        const float v0 = wnb * jb.x + Wb.x * jb.y + Wb.y * jb.z, v1 = Wb.x * jb.x + Wb.z * jb.y, v2 = Wb.y * jb.x + Wb.w * jb.z;
         const float4* jr = jrow(c);
+        const float4* jr2 = two ? jrow(c + 1) : jr;  // without a second contact: finite numbers times v = 0
 #pragma unroll
         for (int k = 0; k < NVP; k++) {
-          const float4 jk = jr[k];
+          const float4 jk = jr[k], jl = jr2[k];
           hrow[k] += u0 * jk.x + u1 * jk.y + u2 * jk.z;
+          hrow[k] += v0 * jl.x + v1 * jl.y + v2 * jl.z;
         }
       }
+      MMZ_STICK(3);  // Hessian rows
       const float dg = me ? dadd : 1.f, rhs0 = me ? -grad : 0.f;
       const float dr = L.topo == 1 ? elim_solve2<1>(hrow, rhs0, dg) : elim_solve2<0>(hrow, rhs0, dg);
       if (me && !done) W_(L.o_dir + lane) = dr;
       __syncwarp();
+      MMZ_STICK(4);  // elimination
       float alpha = 1.f;
       int ls = 0;
       bool exact = false;
@@ -1014,6 +1072,7 @@ struct HEnv {
             ra[2 + i] = cD * rv[2 + i] * rv[2 + i]; rb[2 + i] = cD * rj[2 + i] * rv[2 + i];
           }
         }
+        MMZ_STICK(5);  // M dir, rows of the line search
         bool lsdone = done || !constrained;
         bool flipped = false, lsconv = false;  // did a row change sides between 0 and alpha; did the search converge
         {
@@ -1065,6 +1124,7 @@ struct HEnv {
         exact = !flipped && lsconv && fabsf(alpha - 1.f) < 1e-3f;
         if (exact) alpha = 1.f;  // the minimiser of that quadratic is the Newton step itself
       }
+      MMZ_STICK(6);  // line search
       bool moved = false;
       if (me && !done) {
         const float st = alpha * dr;
@@ -1081,6 +1141,10 @@ struct HEnv {
       __syncwarp();
       const unsigned movedbits = gballot(moved);
       if (!constrained || movedbits == 0 || exact) done = true;
+      MMZ_STICK(7);  // update
+#ifdef MMZ_PHASE_TIMING
+      if (blockIdx.x == 0 && e == 0) atomicAdd(&g_sec[15], 1ull);
+#endif
       if (__all_sync(kAll, done)) break;
     }
     __syncwarp();
@@ -1196,6 +1260,9 @@ struct HEnv {
   MMZ_DI void solve_g3(const TLayout& L, bool warmstart) {
     const int nv = L.nv;
     const bool me = lane < nv;
+#ifdef MMZ_PHASE_TIMING
+    long long stick_ = clock64();
+#endif
     const unsigned limbits = gballot(limD[0] > 0.f || limD[1] > 0.f);
     float mrow[NVP];  // this lane's row of the mass matrix (zero outside its sparsity pattern and outside the model)
     const int rel = me ? dv->dof_rel[lane] : 0;
@@ -1230,6 +1297,7 @@ struct HEnv {
 #pragma unroll
     for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_qacc + k); Ma += t; Mabs += fabsf(t); }
     const unsigned lt = (1u << lane) - 1u;
+    MMZ_STICK(0);
 #pragma unroll 1
     for (int it = 0; it < kTMaxNewton; it++) {
       float grad = Ma - sm_, dadd = 0.f;
@@ -1247,6 +1315,7 @@ struct HEnv {
       }
       contact_pass3(L, L.o_qacc, ncon, ncw, 0);
       __syncwarp();
+      MMZ_STICK(1);
 #pragma unroll 1
       for (int c = 0; c < ncw; c++) {  // gradient J^T f: this lane's entry of every contact that moves its dof
         const int cs = L.o_con + c * L.cstride;
@@ -1258,6 +1327,7 @@ struct HEnv {
         }
       }
       if (gballot(me && fabsf(grad) > tol * mag + 1e-30f) == 0) done = true;
+      MMZ_STICK(2);
       if (__all_sync(kAll, done)) break;
 #pragma unroll 1
       for (int c = 0; c < ncw; c++) {  // contact part of the Hessian row, in shared memory, over the dofs of the mask
@@ -1280,10 +1350,12 @@ struct HEnv {
       float hrow[NVP];
 #pragma unroll
       for (int k = 0; k < NVP; k++) { hrow[k] = mrow[k] + hg[k]; hg[k] = 0.f; }
+      MMZ_STICK(3);
       const float dg = me ? dadd : 1.f, rhs0 = me ? -grad : 0.f;
       const float dr = elim_solve2<0>(hrow, rhs0, dg);
       if (me && !done) W_(L.o_dir + lane) = dr;
       __syncwarp();
+      MMZ_STICK(4);
       float alpha = 1.f;
       int ls = 0;
       bool exact = false;
@@ -1302,6 +1374,7 @@ struct HEnv {
         // the full Newton step crosses no row: it is the minimiser along the direction, no search needed
         flipped = gballot(fl) != 0;
         if (!flipped && !lsdone) { lsdone = true; lsconv = true; }
+        MMZ_STICK(5);
         if (!__all_sync(kAll, lsdone)) {
           const bool searched = !lsdone;
           const float g0 = gsum16(me ? dr * (Ma - sm_) : 0.f), h0 = gsum16(me ? dr * md : 0.f);
@@ -1331,6 +1404,7 @@ struct HEnv {
         exact = !flipped && lsconv && fabsf(alpha - 1.f) < 1e-3f;
         if (exact) alpha = 1.f;  // the minimiser of that quadratic is the Newton step itself
       }
+      MMZ_STICK(6);
       bool moved = false;
       if (me && !done) {
         const float st = alpha * dr;
@@ -1347,6 +1421,10 @@ struct HEnv {
       __syncwarp();
       const unsigned movedbits = gballot(moved);
       if (!constrained || movedbits == 0 || exact) done = true;
+      MMZ_STICK(7);
+#ifdef MMZ_PHASE_TIMING
+      if (blockIdx.x == 0 && e == 0) atomicAdd(&g_sec[15], 1ull);
+#endif
       if (__all_sync(kAll, done)) break;
     }
     __syncwarp();

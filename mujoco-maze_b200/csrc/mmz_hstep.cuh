@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
     for (int i = 0; i < 16; i++) printf(" %u", g_iter_hist[i]);
     printf("\n  per warp solve / wait (kcycles):");
     for (int i = 0; i < 16; i++) printf(" %llu/%llu", g_wsolve[i] / 1000, g_wwait[i] / 1000);
-    printf("\n");
+    printf("\n  solver sections (sum over the warps of block 0, kcycles): prologue %llu contact pass %llu gradient %llu hessian %llu elimination %llu rows %llu line search %llu update %llu | warp iterations %llu\n",
+           g_sec[0] / 1000, g_sec[1] / 1000, g_sec[2] / 1000, g_sec[3] / 1000, g_sec[4] / 1000, g_sec[5] / 1000, g_sec[6] / 1000, g_sec[7] / 1000, g_sec[15]);
   }
 #endif
   HTask<NVP, BOX> T;
@@ -288,7 +289,8 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
         A.done[env] = (uint8_t)bits;
         if (A.info) {
           float* o = A.info + (size_t)env * 4;
-          o[0] = info0; o[1] = info1; o[2] = fwd; o[3] = -cc;
+          if ((reinterpret_cast<uintptr_t>(A.info) & 15) == 0) *reinterpret_cast<float4*>(o) = make_float4(info0, info1, fwd, -cc);
+          else { o[0] = info0; o[1] = info1; o[2] = fwd; o[3] = -cc; }
         }
         if (A.diag)
           for (int k = 0; k < 4; k++) A.diag[(size_t)env * 4 + k] = cn[(L.o_cnt + TN_ITER_SUM + k) * HS + e];

@@ -252,13 +252,16 @@ def test_point_wall_clamp_matches_reference_goldens(torch_cuda):
     print(report)
 
 
+@pytest.mark.parametrize("zero_copy", [True, False])
 @pytest.mark.parametrize("env_id,n", [("AntUMaze-v0", 96), ("AntUMaze-v0", 2500), ("PointUMaze-v0", 5000)])
-def test_step_host_equals_device_step(env_id, n, torch_cuda):
-    """mmz_step_host == mmz_step bit for bit; from 64 blocks on the host call runs as 4 pipelined block ranges
-    (uploads / downloads of one range under the kernel of another), with a ragged last block."""
+def test_step_host_equals_device_step(env_id, n, zero_copy, torch_cuda, monkeypatch):
+    """mmz_step_host == mmz_step bit for bit, with a ragged last block. Pinned buffers: ONE launch whose blocks read the
+    actions and write the results straight through the mapped host addresses. Staged path (MMZ_HOST_ZERO_COPY=0, or
+    pageable buffers): from 64 blocks on, 4 pipelined block ranges (copies of one range under the kernel of another)."""
     from mujoco_maze.backend import BatchedSim
 
     torch = torch_cuda
+    monkeypatch.setenv("MMZ_HOST_ZERO_COPY", "1" if zero_copy else "0")
     model = make_model(env_id)
     rng = np.random.default_rng(5)
     q, v = sample_states(model, env_id, n, rng)
@@ -277,7 +280,7 @@ def test_step_host_equals_device_step(env_id, n, torch_cuda):
     torch.cuda.synchronize()
     assert torch.equal(obs.cpu(), h_obs) and torch.equal(rew.cpu(), h_rew)
     assert torch.equal(done.cpu(), h_done) and torch.equal(info.cpu(), h_info)
-    assert s2.launch_count - launches0 == (1 if n < 1000 else 4)
+    assert s2.launch_count - launches0 == (1 if (n < 1000 or zero_copy) else 4)
     q1, v1, t1 = s1.get_state()
     q2, v2, t2 = s2.get_state()
     assert torch.equal(q1, q2) and torch.equal(v1, v2) and torch.equal(t1, t2)
