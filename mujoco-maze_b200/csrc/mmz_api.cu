@@ -376,6 +376,8 @@ bool configure_h(mmz_env* h, int* rc) {
     // (quaternions, inertias, bias accelerations and forces): the contact records overlay THOSE, as before.
     L.v3 = 1;
     L.cstride = K3_STRIDE;
+    // dofs 0..5 are one free joint: every contact's dof mask holds all six of them or none (bit 2 of topo, solve_g3)
+    if (m.nv >= 6 && m.jnt_type[0] == MMZ_JNT_FREE && m.jnt_dadr[0] == 0) L.topo |= 2;
     L.o_dir = take(nvp);
     L.o_nat = o = round_up(o, 4);
     L.o_cdof = take(6 * L.nv);

@@ -1173,12 +1173,17 @@ struct HEnv {
 #pragma unroll
       for (int off = 1; off < 16; off <<= 1) { const int v = __shfl_up_sync(kAll, incl, off, 16); if (lane >= off) incl += v; }
       const int excl = incl - cnt + total;
+      // K3_JOFF holds ONE word for the passes below: the contact's dof mask (16 bits) and, above it, the offset of its
+      // entries in the pool; 0 for the slots beyond this environment's contacts (the other one of the warp has more)
       if (valid) {
-        if (excl + cnt > L.njac) {  // the pool is full: the contact is dropped (and the overflow reported)
+        const bool full = excl + cnt > L.njac;
+        if (full) {  // the pool is full: the contact is dropped (and the overflow reported)
           W_(cs + K_MPOS) = __int_as_float(0); W_(cs + K_MNEG) = __int_as_float(0);
           IW(L.o_cnt + TN_OVERFLOW) = 1;
         }
-        IW(cs + K3_JOFF) = min(excl, L.njac);
+        IW(cs + K3_JOFF) = full ? 0 : (cmask(cs) | excl << 16);
+      } else if (c < ncw) {
+        IW(cs + K3_JOFF) = 0;
       }
       total += __shfl_sync(kAll, incl, 15, 16);
     }
@@ -1199,7 +1204,7 @@ struct HEnv {
       const float mu = W_(cs + K_MU);
       const float jn = dot3(fr, v), jt1 = mu * dot3(fr + 3, v), jt2 = mu * dot3(fr + 6, v);
       if (c < ncon && (mask >> lane & 1))
-        jg[IW(cs + K3_JOFF) + __popc(mask & ((1 << lane) - 1))] = make_float4(jn, jt1, jt2, fabsf(jn) + fabsf(jt1) + fabsf(jt2));
+        jg[(IW(cs + K3_JOFF) >> 16) + __popc(mask & ((1 << lane) - 1))] = make_float4(jn, jt1, jt2, fabsf(jn) + fabsf(jt1) + fabsf(jt2));
     }
   }
   // lane = contact (16 per trip): J x over the dofs of the contact's mask. which 0: x = qacc -> J a - aref, force and
@@ -1212,13 +1217,31 @@ struct HEnv {
       float4 F = make_float4(0.f, 0.f, 0.f, 0.f), Wt = F;
       if (c < ncon) {
         const int cs = L.o_con + c * L.cstride;
-        const float4* jr = jg + IW(cs + K3_JOFF);
+        const int mj = IW(cs + K3_JOFF);
+        const float4* jr = jg + (mj >> 16);
+        unsigned bits = mj & 0xffff;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, sa = 0.f;
+        if (NVP >= 6 && (L.topo & 2) && (bits & 0x3fu) == 0x3fu) {  // the six dofs of the free root: entries 0..5, no bit walk
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            const float4 j = jr[k];
+            const float x = W_(xoff + k);
+            s0 = fmaf(j.x, x, s0); s1 = fmaf(j.y, x, s1); s2 = fmaf(j.z, x, s2); sa = fmaf(j.w, fabsf(x), sa);
+          }
+          jr += 6; bits &= ~0x3fu;
+        }
 #pragma unroll 1
-        for (int bits = cmask(cs); bits; bits &= bits - 1) {
-          const float4 j = *jr++;
-          const float x = W_(xoff + __ffs(bits) - 1);
+        while (bits) {  // two entries per trip (their loads in flight together; same order of additions as one by one)
+          const int k0 = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const bool two = bits != 0;
+          const int k1 = two ? __ffs(bits) - 1 : k0;
+          bits &= bits - 1;
+          const float4 j = jr[0], j1 = jr[1];  // (jr[1] may belong to the next contact: unused then)
+          const float x = W_(xoff + k0), x1 = W_(xoff + k1);
+          jr += 2;
           s0 = fmaf(j.x, x, s0); s1 = fmaf(j.y, x, s1); s2 = fmaf(j.z, x, s2); sa = fmaf(j.w, fabsf(x), sa);
+          if (two) { s0 = fmaf(j1.x, x1, s0); s1 = fmaf(j1.y, x1, s1); s2 = fmaf(j1.z, x1, s2); sa = fmaf(j1.w, fabsf(x1), sa); }
         }
         if (which == 1) {
           W_(cs + K3_JV) = s0 + s1; W_(cs + K3_JV + 1) = s0 - s1; W_(cs + K3_JV + 2) = s0 + s2; W_(cs + K3_JV + 3) = s0 - s2;
@@ -1317,39 +1340,63 @@ struct HEnv {
       __syncwarp();
       MMZ_STICK(1);
 #pragma unroll 1
-      for (int c = 0; c < ncw; c++) {  // gradient J^T f: this lane's entry of every contact that moves its dof
+      for (int c = 0; c < ncw; c += 2) {  // gradient J^T f: this lane's entry of every contact that moves its dof (two per trip)
         const int cs = L.o_con + c * L.cstride;
-        const unsigned mask = c < ncon ? (unsigned)cmask(cs) : 0u;
-        if (mask >> lane & 1) {
-          const float4 j = jg[IW(cs + K3_JOFF) + __popc(mask & lt)], F = fg[2 * c];
-          grad += j.x * F.x + j.y * F.y + j.z * F.z;
-          mag = fmaf(j.w, F.w, mag);
-        }
+        const unsigned mj = (unsigned)IW(cs + K3_JOFF), mj1 = c + 1 < ncw ? (unsigned)IW(cs + L.cstride + K3_JOFF) : 0u;
+        const bool in0 = mj >> lane & 1, in1 = mj1 >> lane & 1;
+        float4 j = make_float4(0.f, 0.f, 0.f, 0.f), F = j, j1 = j, F1 = j;
+        if (in0) { j = jg[(mj >> 16) + __popc(mj & lt)]; F = fg[2 * c]; }
+        if (in1) { j1 = jg[(mj1 >> 16) + __popc(mj1 & lt)]; F1 = fg[2 * c + 2]; }
+        if (in0) { grad += j.x * F.x + j.y * F.y + j.z * F.z; mag = fmaf(j.w, F.w, mag); }
+        if (in1) { grad += j1.x * F1.x + j1.y * F1.y + j1.z * F1.z; mag = fmaf(j1.w, F1.w, mag); }
       }
       if (gballot(me && fabsf(grad) > tol * mag + 1e-30f) == 0) done = true;
       MMZ_STICK(2);
       if (__all_sync(kAll, done)) break;
+      // Contact part of the Hessian row over the dofs of each contact's mask. The six dofs of a free root (when the model
+      // has one, every mask holds all six or none: they are its entries 0..5) go to REGISTERS, whatever else the contact
+      // moves - a leg's hip and ankle, a block's slides - to the row in shared memory (dynamic column), two per trip.
+      constexpr int NR = NVP >= 6 ? 6 : 1;
+      float hacc[NR];
+#pragma unroll
+      for (int k = 0; k < NR; k++) hacc[k] = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < ncw; c++) {  // contact part of the Hessian row, in shared memory, over the dofs of the mask
+      for (int c = 0; c < ncw; c++) {
         const float4 Wt = fg[2 * c + 1];
+        const unsigned mj = (unsigned)IW(L.o_con + c * L.cstride + K3_JOFF);
         const float wnn = Wt.z + Wt.w;
         if (!__any_sync(kAll, wnn != 0.f)) continue;  // no active row in this contact, in either environment
-        const int cs = L.o_con + c * L.cstride;
-        const unsigned mask = (c < ncon && wnn != 0.f) ? (unsigned)cmask(cs) : 0u;
-        if (mask >> lane & 1) {
-          const float4* jr = jg + IW(cs + K3_JOFF);
-          const float4 j = jr[__popc(mask & lt)];
+        unsigned bits = wnn != 0.f ? mj & 0xffffu : 0u;
+        if (bits >> lane & 1) {
+          const float4* jr = jg + (mj >> 16);
+          const float4 j = jr[__popc(bits & lt)];
           const float u0 = wnn * j.x + Wt.x * j.y + Wt.y * j.z, u1 = Wt.x * j.x + Wt.z * j.y, u2 = Wt.y * j.x + Wt.w * j.z;
+          if (NVP >= 6 && (L.topo & 2) && (bits & 0x3fu) == 0x3fu) {
+#pragma unroll
+            for (int k = 0; k < NR; k++) {
+              const float4 jk = jr[k];
+              hacc[k] += u0 * jk.x + u1 * jk.y + u2 * jk.z;
+            }
+            jr += 6; bits &= ~0x3fu;
+          }
 #pragma unroll 1
-          for (unsigned bits = mask; bits; bits &= bits - 1) {
-            const float4 jk = *jr++;
-            hg[__ffs(bits) - 1] += u0 * jk.x + u1 * jk.y + u2 * jk.z;
+          while (bits) {
+            const int k0 = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const bool two = bits != 0;
+            const int k1 = two ? __ffs(bits) - 1 : k0;
+            bits &= bits - 1;
+            const float4 jk = jr[0], jl = jr[1];  // (jr[1] may belong to the next contact: unused then)
+            const float h0 = hg[k0], h1 = hg[k1];
+            jr += 2;
+            hg[k0] = h0 + (u0 * jk.x + u1 * jk.y + u2 * jk.z);
+            if (two) hg[k1] = h1 + (u0 * jl.x + u1 * jl.y + u2 * jl.z);
           }
         }
       }
       float hrow[NVP];
 #pragma unroll
-      for (int k = 0; k < NVP; k++) { hrow[k] = mrow[k] + hg[k]; hg[k] = 0.f; }
+      for (int k = 0; k < NVP; k++) { hrow[k] = mrow[k] + (k < NR && NVP >= 6 ? hg[k] + hacc[k] : hg[k]); hg[k] = 0.f; }
       MMZ_STICK(3);
       const float dg = me ? dadd : 1.f, rhs0 = me ? -grad : 0.f;
       const float dr = elim_solve2<0>(hrow, rhs0, dg);
