@@ -378,6 +378,12 @@ bool configure_h(mmz_env* h, int* rc) {
     L.cstride = K3_STRIDE;
     // dofs 0..5 are one free joint: every contact's dof mask holds all six of them or none (bit 2 of topo, solve_g3)
     if (m.nv >= 6 && m.jnt_type[0] == MMZ_JNT_FREE && m.jnt_dadr[0] == 0) L.topo |= 2;
+    {  // the Ant's dof tree (a free root, four 2-dof chains) and a second tree, the 2-dof chain (14, 15) of one movable block: bit 4
+      bool ab = m.nv == 16 && (L.topo & 2);
+      for (int d = 0; d < m.nv && ab; d++)
+        ab = m.dof_parent[d] == (d < 6 ? d - 1 : d == 14 ? -1 : (d & 1) ? d - 1 : 5);
+      if (ab) L.topo |= 4;
+    }
     L.o_dir = take(nvp);
     L.o_nat = o = round_up(o, 4);
     L.o_cdof = take(6 * L.nv);

@@ -96,7 +96,9 @@ struct TLayout {
   // float4 arrays in natural [environment][contact] order. They OVERLAY the slots [o_nat, o_con) of the [slot][33]
   // workspace, whose arrays are all dead while the solver runs.
   int v2, o_nat, jes, fa_off;  // first slot (multiple of 4); float4s per environment of the Jacobian area; float4 offset of FA
-  int topo;                    // 1: the dof tree is the Ant's (free root + 2-dof chains): sparse elimination order (elim_solve2)
+  int topo;                    // 1 (solver v2): the dof tree is the Ant's (free root + 2-dof chains): sparse elimination order (elim_solve2).
+                               // Solver v3, bits: 2 = dofs 0..5 are one free joint (every contact mask holds all six or none),
+                               // 4 = the Ant's tree + the 2-dof chain (14, 15) of one movable block (elim_solve2<3>)
   int v3, njac, es;            // solver v3 (box instances): float4 Jacobian entries per environment; float4s per environment of its natural area
 };
 
@@ -815,16 +817,18 @@ struct HEnv {
   template <int TOPO>
   MMZ_DI float elim_solve2(float (&h)[NVP], float rhs, float dg) const {
     float invd = 1.f;
-    if (TOPO == 1 && NVP == 14) {
+    constexpr bool kSide = (TOPO == 1 && NVP == 14) || (TOPO == 3 && NVP == 16);
+    constexpr int NP = TOPO == 3 ? 5 : 4;  // TOPO 3: the Ant's tree and a second tree, the 2-dof chain (14, 15) of a movable block
+    if (kSide) {
       // The four ankle rows do not couple with each other, and once they are gone neither do the four hip rows: their
       // pivots run SIDE BY SIDE (a lane that is one of the four pivots has a zero multiplier for the other three, so the
       // rows the shuffles read are the ones a one-by-one elimination would read). The chain of dependent (shuffle,
       // reciprocal, multiply-add) steps is 1 + 1 + 6 long instead of 14.
 #pragma unroll
       for (int ph = 0; ph < 2; ph++) {
-        float f[4], t[4];
+        float f[NP], t[NP];
 #pragma unroll
-        for (int m = 0; m < 4; m++) {
+        for (int m = 0; m < NP; m++) {
           const int j = 7 + 2 * m - ph;
           const bool own = lane == j;
           float hd = h[j];
@@ -838,9 +842,9 @@ struct HEnv {
           t[m] = __shfl_sync(kAll, rhs, j, 16);
         }
 #pragma unroll
-        for (int m = 0; m < 4; m++) rhs -= f[m] * t[m];
+        for (int m = 0; m < NP; m++) rhs -= f[m] * t[m];
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
+        for (int k = 0; k < 6; k++) {  // (the block's chain does not hang off the root: m < 4)
 #pragma unroll
           for (int m = 0; m < 4; m++) t[m] = __shfl_sync(kAll, h[k], 7 + 2 * m - ph, 16);
 #pragma unroll
@@ -848,13 +852,13 @@ struct HEnv {
         }
         if (ph == 0) {
 #pragma unroll
-          for (int m = 0; m < 4; m++) h[6 + 2 * m] -= f[m] * __shfl_sync(kAll, h[6 + 2 * m], 7 + 2 * m, 16);
+          for (int m = 0; m < NP; m++) h[6 + 2 * m] -= f[m] * __shfl_sync(kAll, h[6 + 2 * m], 7 + 2 * m, 16);
         }
       }
     }
 #pragma unroll
-    for (int jj = (TOPO == 1 && NVP == 14) ? 8 : 0; jj < NVP; jj++) {
-      const int j = TOPO == 1 ? NVP - 1 - jj : jj;
+    for (int jj = kSide ? NVP - 6 : 0; jj < NVP; jj++) {
+      const int j = TOPO != 0 ? NVP - 1 - jj : jj;
       const bool own = lane == j;
       float hd = h[j];
       asm("" : "+f"(hd));
@@ -866,7 +870,7 @@ struct HEnv {
       const float f = own ? 0.f : hd * inv;
       invd = own ? inv : invd;
       rhs -= f * rj;
-      if (TOPO == 1) {
+      if (TOPO != 0) {
 #pragma unroll
         for (int k = 0; k < NVP; k++) {
           const bool anc = j < 6 ? k < j : (k < 6 || ((j & 1) && k == j - 1));
@@ -1162,8 +1166,11 @@ struct HEnv {
   // row is accumulated in shared memory (dynamic column index), over the dofs of the mask only, then added to the
   // mass-matrix row in registers. Line-search rows of the contacts stay in their records (any number of contacts).
   MMZ_DI int cmask(int cs) const { return __float_as_int(W_(cs + K_MPOS)) | __float_as_int(W_(cs + K_MNEG)); }
-  MMZ_DI void build_jac3(const TLayout& L, const float (&cd)[6], int ncon, int ncw) {
+  // Returns whether some contact of this environment moves dofs of BOTH trees of an Ant-and-block model (dofs 0..13 and
+  // 14, 15): only then does the Hessian couple them (elim_solve2<3> otherwise).
+  MMZ_DI bool build_jac3(const TLayout& L, const float (&cd)[6], int ncon, int ncw) {
     int total = 0;
+    bool cross = false;
 #pragma unroll 1
     for (int t0 = 0; t0 < ncw; t0 += 16) {  // offsets: lane = contact
       const int c = t0 + lane, cs = L.o_con + c * L.cstride;
@@ -1181,7 +1188,9 @@ struct HEnv {
           W_(cs + K_MPOS) = __int_as_float(0); W_(cs + K_MNEG) = __int_as_float(0);
           IW(L.o_cnt + TN_OVERFLOW) = 1;
         }
-        IW(cs + K3_JOFF) = full ? 0 : (cmask(cs) | excl << 16);
+        const int mk = cmask(cs);
+        cross |= !full && (mk & 0x3fff) && (mk & 0xc000);
+        IW(cs + K3_JOFF) = full ? 0 : (mk | excl << 16);
       } else if (c < ncw) {
         IW(cs + K3_JOFF) = 0;
       }
@@ -1206,6 +1215,7 @@ struct HEnv {
       if (c < ncon && (mask >> lane & 1))
         jg[(IW(cs + K3_JOFF) >> 16) + __popc(mask & ((1 << lane) - 1))] = make_float4(jn, jt1, jt2, fabsf(jn) + fabsf(jt1) + fabsf(jt2));
     }
+    return gballot(cross) != 0;
   }
   // lane = contact (16 per trip): J x over the dofs of the contact's mask. which 0: x = qacc -> J a - aref, force and
   // Hessian weights of the active rows; which 1: x = direction -> J dir per pyramid row into the record
@@ -1293,6 +1303,7 @@ struct HEnv {
     for (int k = 0; k < NVP; k++) mrow[k] = (rel >> k & 1) ? W_(L.o_M + lane * L.ldm + k) : 0.f;
     const float sm_ = me ? W_(L.o_smooth + lane) : 0.f;
     int ncon, ncw;
+    bool coupled = true;
     {
       float cd[6];
 #pragma unroll
@@ -1303,8 +1314,10 @@ struct HEnv {
       ncw = max(ncon, __shfl_xor_sync(kAll, ncon, 16));  // the two environments of the warp
 #pragma unroll
       for (int k = 0; k < NVP; k++) hg[k] = 0.f;
-      build_jac3(L, cd, ncon, ncw);
+      coupled = build_jac3(L, cd, ncon, ncw);
     }
+    // the Ant's tree and the block's chain eliminate side by side unless a contact couples them in either environment
+    const bool sparse = NVP == 16 && (L.topo & 4) && !__any_sync(kAll, coupled);
     const bool constrained = ncon > 0 || limbits != 0;
     float al = (warmstart && me) ? W_(L.o_qacc + lane) : 0.f;
     if (!(fabsf(al) < kMaxVal)) al = 0.f;  // a blown-up environment restarts from zero
@@ -1399,7 +1412,9 @@ struct HEnv {
       for (int k = 0; k < NVP; k++) { hrow[k] = mrow[k] + (k < NR && NVP >= 6 ? hg[k] + hacc[k] : hg[k]); hg[k] = 0.f; }
       MMZ_STICK(3);
       const float dg = me ? dadd : 1.f, rhs0 = me ? -grad : 0.f;
-      const float dr = elim_solve2<0>(hrow, rhs0, dg);
+      float dr;
+      if constexpr (NVP == 16) dr = sparse ? elim_solve2<3>(hrow, rhs0, dg) : elim_solve2<0>(hrow, rhs0, dg);
+      else dr = elim_solve2<0>(hrow, rhs0, dg);
       if (me && !done) W_(L.o_dir + lane) = dr;
       __syncwarp();
       MMZ_STICK(4);
