@@ -308,6 +308,7 @@ bool configure_h(mmz_env* h, int* rc) {
   }
   TLayout L;
   memset(&L, 0, sizeof L);
+  L.tail0 = -1;
   L.nb = m.nbody; L.nj = m.njnt; L.nv = m.nv; L.nq = m.nq; L.nu = m.nu; L.ng = m.ngeom; L.nobj = m.nobj; L.obs_dim = m.obs_dim;
   L.nlatch = m.nobj + m.nviewb; L.obs_core = m.obs_dim - m.view_dim;
   int nlev = 0;
@@ -383,6 +384,11 @@ bool configure_h(mmz_env* h, int* rc) {
       for (int d = 0; d < m.nv && ab; d++)
         ab = m.dof_parent[d] == (d < 6 ? d - 1 : d == 14 ? -1 : (d & 1) ? d - 1 : 5);
       if (ab) L.topo |= 4;
+    }
+    {  // the last dof tree has exactly two dofs (a movable block on two slides): its own contacts are handled lane = contact
+      int t0 = m.nv - 1;
+      while (t0 > 0 && m.dof_parent[t0] >= 0) t0--;
+      L.tail0 = (m.nv >= 3 && m.nv - t0 == 2 && t0 > 0) ? t0 : -1;
     }
     L.o_dir = take(nvp);
     L.o_nat = o = round_up(o, 4);

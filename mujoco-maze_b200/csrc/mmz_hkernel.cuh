@@ -100,6 +100,7 @@ struct TLayout {
                                // Solver v3, bits: 2 = dofs 0..5 are one free joint (every contact mask holds all six or none),
                                // 4 = the Ant's tree + the 2-dof chain (14, 15) of one movable block (elim_solve2<3>)
   int v3, njac, es;            // solver v3 (box instances): float4 Jacobian entries per environment; float4s per environment of its natural area
+  int tail0;                   // solver v3: the last dof tree has exactly two dofs, tail0 and tail0 + 1 (a movable block's slides), else -1
 };
 
 struct TArgs {
@@ -1168,9 +1169,12 @@ struct HEnv {
   MMZ_DI int cmask(int cs) const { return __float_as_int(W_(cs + K_MPOS)) | __float_as_int(W_(cs + K_MNEG)); }
   // Returns whether some contact of this environment moves dofs of BOTH trees of an Ant-and-block model (dofs 0..13 and
   // 14, 15): only then does the Hessian couple them (elim_solve2<3> otherwise).
-  MMZ_DI bool build_jac3(const TLayout& L, const float (&cd)[6], int ncon, int ncw) {
-    int total = 0;
+  // `nnb`: one past the last contact, in either environment of the warp, that moves anything but the two dofs of the
+  // tail tree (the block's own contacts come last in the contact order; the Hessian pass handles them lane = contact).
+  MMZ_DI bool build_jac3(const TLayout& L, const float (&cd)[6], int ncon, int ncw, int* nnb) {
+    int total = 0, last = 0;
     bool cross = false;
+    const int tailmask = L.tail0 >= 0 ? 3 << L.tail0 : -1;
 #pragma unroll 1
     for (int t0 = 0; t0 < ncw; t0 += 16) {  // offsets: lane = contact
       const int c = t0 + lane, cs = L.o_con + c * L.cstride;
@@ -1190,6 +1194,7 @@ struct HEnv {
         }
         const int mk = cmask(cs);
         cross |= !full && (mk & 0x3fff) && (mk & 0xc000);
+        if (!full && mk != tailmask) last = c + 1;
         IW(cs + K3_JOFF) = full ? 0 : (mk | excl << 16);
       } else if (c < ncw) {
         IW(cs + K3_JOFF) = 0;
@@ -1215,6 +1220,7 @@ struct HEnv {
       if (c < ncon && (mask >> lane & 1))
         jg[(IW(cs + K3_JOFF) >> 16) + __popc(mask & ((1 << lane) - 1))] = make_float4(jn, jt1, jt2, fabsf(jn) + fabsf(jt1) + fabsf(jt2));
     }
+    *nnb = __reduce_max_sync(kAll, last);
     return gballot(cross) != 0;
   }
   // lane = contact (16 per trip): J x over the dofs of the contact's mask. which 0: x = qacc -> J a - aref, force and
@@ -1302,7 +1308,7 @@ struct HEnv {
 #pragma unroll
     for (int k = 0; k < NVP; k++) mrow[k] = (rel >> k & 1) ? W_(L.o_M + lane * L.ldm + k) : 0.f;
     const float sm_ = me ? W_(L.o_smooth + lane) : 0.f;
-    int ncon, ncw;
+    int ncon, ncw, nnb = 0;
     bool coupled = true;
     {
       float cd[6];
@@ -1314,7 +1320,7 @@ struct HEnv {
       ncw = max(ncon, __shfl_xor_sync(kAll, ncon, 16));  // the two environments of the warp
 #pragma unroll
       for (int k = 0; k < NVP; k++) hg[k] = 0.f;
-      coupled = build_jac3(L, cd, ncon, ncw);
+      coupled = build_jac3(L, cd, ncon, ncw, &nnb);
     }
     // the Ant's tree and the block's chain eliminate side by side unless a contact couples them in either environment
     const bool sparse = NVP == 16 && (L.topo & 4) && !__any_sync(kAll, coupled);
@@ -1373,13 +1379,41 @@ struct HEnv {
       float hacc[NR];
 #pragma unroll
       for (int k = 0; k < NR; k++) hacc[k] = 0.f;
+      const unsigned tailmask = L.tail0 >= 0 ? 3u << L.tail0 : 0u;
+      if (L.tail0 >= 0) {
+        // The contacts that move only the two dofs (a, b) of the tail tree - a block's four corners on the floor, its
+        // points on the walls - with lane = CONTACT, all at once: each lane forms the 2 x 2 contribution J^T W J of its
+        // contact, three sums over the lanes, and the lanes of a and b add them to their rows.
+        float haa = 0.f, hab = 0.f, hbb = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < ncw; c++) {
+        for (int t0 = 0; t0 < ncw; t0 += 16) {
+          const int c = t0 + lane;
+          if (c < ncon) {
+            const unsigned mj = (unsigned)IW(L.o_con + c * L.cstride + K3_JOFF);
+            if ((mj & 0xffffu) == tailmask) {
+              const float4 Wt = fg[2 * c + 1], ja = jg[mj >> 16], jb = jg[(mj >> 16) + 1];
+              const float wnn = Wt.z + Wt.w;
+              const float a0 = wnn * ja.x + Wt.x * ja.y + Wt.y * ja.z, a1 = Wt.x * ja.x + Wt.z * ja.y, a2 = Wt.y * ja.x + Wt.w * ja.z;
+              const float b0 = wnn * jb.x + Wt.x * jb.y + Wt.y * jb.z, b1 = Wt.x * jb.x + Wt.z * jb.y, b2 = Wt.y * jb.x + Wt.w * jb.z;
+              haa += a0 * ja.x + a1 * ja.y + a2 * ja.z;
+              hab += a0 * jb.x + a1 * jb.y + a2 * jb.z;
+              hbb += b0 * jb.x + b1 * jb.y + b2 * jb.z;
+            }
+          }
+        }
+        if (__any_sync(kAll, haa != 0.f || hbb != 0.f)) {
+          haa = gsum16(haa); hab = gsum16(hab); hbb = gsum16(hbb);
+          if (lane == L.tail0) { hg[L.tail0] += haa; hg[L.tail0 + 1] += hab; }
+          if (lane == L.tail0 + 1) { hg[L.tail0] += hab; hg[L.tail0 + 1] += hbb; }
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < nnb; c++) {
         const float4 Wt = fg[2 * c + 1];
         const unsigned mj = (unsigned)IW(L.o_con + c * L.cstride + K3_JOFF);
         const float wnn = Wt.z + Wt.w;
-        if (!__any_sync(kAll, wnn != 0.f)) continue;  // no active row in this contact, in either environment
-        unsigned bits = wnn != 0.f ? mj & 0xffffu : 0u;
+        unsigned bits = (wnn != 0.f && (mj & 0xffffu) != tailmask) ? mj & 0xffffu : 0u;
+        if (!__any_sync(kAll, bits != 0u)) continue;  // no active row in this contact, in either environment
         if (bits >> lane & 1) {
           const float4* jr = jg + (mj >> 16);
           const float4 j = jr[__popc(bits & lt)];

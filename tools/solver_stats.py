@@ -29,3 +29,6 @@ for k in range(steps):
         it = d[:, 0]
         print(f"step {k}: newton/step mean {it.mean():.2f} p50 {np.median(it):.0f} p99 {np.quantile(it, .99):.0f} max {it.max():.0f} | "
               f"line-search/step {d[:, 1].mean():.2f} | max contacts mean {d[:, 2].mean():.2f} | capped {d[:, 3].sum():.0f}")
+    if k == steps - 1:
+        cm = d[:, 2].astype(int)
+        print("max contacts per env-step, histogram:", {int(v): int((cm == v).sum()) for v in np.unique(cm)})
