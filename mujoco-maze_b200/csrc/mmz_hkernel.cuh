@@ -1202,10 +1202,13 @@ struct HEnv {
       total += __shfl_sync(kAll, incl, 15, 16);
     }
     __syncwarp();
+    const int nn = __reduce_max_sync(kAll, last);
+    *nnb = nn;
 #pragma unroll 1
-    for (int c = 0; c < ncw; c++) {  // entries: lane = dof
+    for (int c = 0; c < nn; c++) {  // entries: lane = dof
       const int cs = L.o_con + c * L.cstride;
-      const int mp = __float_as_int(W_(cs + K_MPOS)), mn = __float_as_int(W_(cs + K_MNEG)), mask = mp | mn;
+      const int mp = __float_as_int(W_(cs + K_MPOS)), mn = __float_as_int(W_(cs + K_MNEG));
+      const int mask = (mp | mn) == tailmask ? 0 : (mp | mn);  // (tail-only contacts: below)
       const float s = (float)(mp >> lane & 1) - (float)(mn >> lane & 1);
       float p[3], fr[9], wxp[3];
 #pragma unroll
@@ -1220,7 +1223,37 @@ struct HEnv {
       if (c < ncon && (mask >> lane & 1))
         jg[(IW(cs + K3_JOFF) >> 16) + __popc(mask & ((1 << lane) - 1))] = make_float4(jn, jt1, jt2, fabsf(jn) + fabsf(jt1) + fabsf(jt2));
     }
-    *nnb = __reduce_max_sync(kAll, last);
+    if (L.tail0 >= 0) {  // the two entries of every tail-only contact, lane = contact (the motion axes of the two dofs by shuffle)
+      float ca[6], cb[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { ca[k] = __shfl_sync(kAll, cd[k], L.tail0, 16); cb[k] = __shfl_sync(kAll, cd[k], L.tail0 + 1, 16); }
+#pragma unroll 1
+      for (int t0 = 0; t0 < ncw; t0 += 16) {
+        const int c = t0 + lane, cs = L.o_con + c * L.cstride;
+        if (c >= ncon) continue;
+        const int mp = __float_as_int(W_(cs + K_MPOS)), mn = __float_as_int(W_(cs + K_MNEG));
+        if ((mp | mn) != tailmask) continue;
+        float p[3], fr[9];
+#pragma unroll
+        for (int k = 0; k < 3; k++) p[k] = W_(cs + K_POS + k);
+#pragma unroll
+        for (int k = 0; k < 6; k++) fr[k] = W_(cs + K_N + k);
+        cross3(fr + 6, fr, fr + 3);
+        const float mu = W_(cs + K_MU);
+        float4* out = jg + (IW(cs + K3_JOFF) >> 16);
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+          const float* cw = w == 0 ? ca : cb;
+          const int d = L.tail0 + w;
+          const float s = (float)(mp >> d & 1) - (float)(mn >> d & 1);
+          float wxp[3];
+          cross3(wxp, cw, p);
+          const float v[3] = {s * (cw[3] + wxp[0]), s * (cw[4] + wxp[1]), s * (cw[5] + wxp[2])};
+          const float jn = dot3(fr, v), jt1 = mu * dot3(fr + 3, v), jt2 = mu * dot3(fr + 6, v);
+          out[w] = make_float4(jn, jt1, jt2, fabsf(jn) + fabsf(jt1) + fabsf(jt2));
+        }
+      }
+    }
     return gballot(cross) != 0;
   }
   // lane = contact (16 per trip): J x over the dofs of the contact's mask. which 0: x = qacc -> J a - aref, force and
@@ -1357,12 +1390,46 @@ struct HEnv {
       }
       contact_pass3(L, L.o_qacc, ncon, ncw, 0);
       __syncwarp();
+      // The contacts that move only the two dofs (a, b) of the tail tree - a block's four corners on the floor, its points
+      // on the walls - with lane = CONTACT, all at once: each lane forms J^T f and the 2 x 2 block J^T W J of its contact,
+      // seven sums over the lanes, and the lanes of a and b take them (the Hessian part is added to their rows below).
+      const unsigned tailmask = L.tail0 >= 0 ? 3u << L.tail0 : 0u;
+      float tH0 = 0.f, tH1 = 0.f;
+      if (L.tail0 >= 0) {
+        float ga = 0.f, gb = 0.f, ma = 0.f, mb = 0.f, haa = 0.f, hab = 0.f, hbb = 0.f;
+        bool any = false;
+#pragma unroll 1
+        for (int t0 = 0; t0 < ncw; t0 += 16) {
+          const int c = t0 + lane;
+          if (c < ncon) {
+            const unsigned mj = (unsigned)IW(L.o_con + c * L.cstride + K3_JOFF);
+            if ((mj & 0xffffu) == tailmask) {
+              const float4 F = fg[2 * c], Wt = fg[2 * c + 1], ja = jg[mj >> 16], jb = jg[(mj >> 16) + 1];
+              const float wnn = Wt.z + Wt.w;
+              const float a0 = wnn * ja.x + Wt.x * ja.y + Wt.y * ja.z, a1 = Wt.x * ja.x + Wt.z * ja.y, a2 = Wt.y * ja.x + Wt.w * ja.z;
+              const float b0 = wnn * jb.x + Wt.x * jb.y + Wt.y * jb.z, b1 = Wt.x * jb.x + Wt.z * jb.y, b2 = Wt.y * jb.x + Wt.w * jb.z;
+              haa += a0 * ja.x + a1 * ja.y + a2 * ja.z;
+              hab += a0 * jb.x + a1 * jb.y + a2 * jb.z;
+              hbb += b0 * jb.x + b1 * jb.y + b2 * jb.z;
+              ga += ja.x * F.x + ja.y * F.y + ja.z * F.z; ma = fmaf(ja.w, F.w, ma);
+              gb += jb.x * F.x + jb.y * F.y + jb.z * F.z; mb = fmaf(jb.w, F.w, mb);
+              any = true;
+            }
+          }
+        }
+        if (__any_sync(kAll, any)) {
+          ga = gsum16(ga); gb = gsum16(gb); ma = gsum16(ma); mb = gsum16(mb);
+          haa = gsum16(haa); hab = gsum16(hab); hbb = gsum16(hbb);
+          if (lane == L.tail0) { grad += ga; mag += ma; tH0 = haa; tH1 = hab; }
+          if (lane == L.tail0 + 1) { grad += gb; mag += mb; tH0 = hab; tH1 = hbb; }
+        }
+      }
       MMZ_STICK(1);
 #pragma unroll 1
-      for (int c = 0; c < ncw; c += 2) {  // gradient J^T f: this lane's entry of every contact that moves its dof (two per trip)
+      for (int c = 0; c < nnb; c += 2) {  // gradient J^T f: this lane's entry of every contact that moves its dof (two per trip)
         const int cs = L.o_con + c * L.cstride;
-        const unsigned mj = (unsigned)IW(cs + K3_JOFF), mj1 = c + 1 < ncw ? (unsigned)IW(cs + L.cstride + K3_JOFF) : 0u;
-        const bool in0 = mj >> lane & 1, in1 = mj1 >> lane & 1;
+        const unsigned mj = (unsigned)IW(cs + K3_JOFF), mj1 = c + 1 < nnb ? (unsigned)IW(cs + L.cstride + K3_JOFF) : 0u;
+        const bool in0 = (mj >> lane & 1) && (mj & 0xffffu) != tailmask, in1 = (mj1 >> lane & 1) && (mj1 & 0xffffu) != tailmask;
         float4 j = make_float4(0.f, 0.f, 0.f, 0.f), F = j, j1 = j, F1 = j;
         if (in0) { j = jg[(mj >> 16) + __popc(mj & lt)]; F = fg[2 * c]; }
         if (in1) { j1 = jg[(mj1 >> 16) + __popc(mj1 & lt)]; F1 = fg[2 * c + 2]; }
@@ -1379,34 +1446,7 @@ struct HEnv {
       float hacc[NR];
 #pragma unroll
       for (int k = 0; k < NR; k++) hacc[k] = 0.f;
-      const unsigned tailmask = L.tail0 >= 0 ? 3u << L.tail0 : 0u;
-      if (L.tail0 >= 0) {
-        // The contacts that move only the two dofs (a, b) of the tail tree - a block's four corners on the floor, its
-        // points on the walls - with lane = CONTACT, all at once: each lane forms the 2 x 2 contribution J^T W J of its
-        // contact, three sums over the lanes, and the lanes of a and b add them to their rows.
-        float haa = 0.f, hab = 0.f, hbb = 0.f;
-#pragma unroll 1
-        for (int t0 = 0; t0 < ncw; t0 += 16) {
-          const int c = t0 + lane;
-          if (c < ncon) {
-            const unsigned mj = (unsigned)IW(L.o_con + c * L.cstride + K3_JOFF);
-            if ((mj & 0xffffu) == tailmask) {
-              const float4 Wt = fg[2 * c + 1], ja = jg[mj >> 16], jb = jg[(mj >> 16) + 1];
-              const float wnn = Wt.z + Wt.w;
-              const float a0 = wnn * ja.x + Wt.x * ja.y + Wt.y * ja.z, a1 = Wt.x * ja.x + Wt.z * ja.y, a2 = Wt.y * ja.x + Wt.w * ja.z;
-              const float b0 = wnn * jb.x + Wt.x * jb.y + Wt.y * jb.z, b1 = Wt.x * jb.x + Wt.z * jb.y, b2 = Wt.y * jb.x + Wt.w * jb.z;
-              haa += a0 * ja.x + a1 * ja.y + a2 * ja.z;
-              hab += a0 * jb.x + a1 * jb.y + a2 * jb.z;
-              hbb += b0 * jb.x + b1 * jb.y + b2 * jb.z;
-            }
-          }
-        }
-        if (__any_sync(kAll, haa != 0.f || hbb != 0.f)) {
-          haa = gsum16(haa); hab = gsum16(hab); hbb = gsum16(hbb);
-          if (lane == L.tail0) { hg[L.tail0] += haa; hg[L.tail0 + 1] += hab; }
-          if (lane == L.tail0 + 1) { hg[L.tail0] += hab; hg[L.tail0 + 1] += hbb; }
-        }
-      }
+      if (L.tail0 >= 0 && (lane == L.tail0 || lane == L.tail0 + 1)) { hg[L.tail0] += tH0; hg[L.tail0 + 1] += tH1; }  // (the tail pass above)
 #pragma unroll 1
       for (int c = 0; c < nnb; c++) {
         const float4 Wt = fg[2 * c + 1];
