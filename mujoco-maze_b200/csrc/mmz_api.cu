@@ -406,7 +406,10 @@ bool configure_h(mmz_env* h, int* rc) {
     const int avail = (dev_smem - round_up(L.model_bytes, 128) - static_smem) / (HS * 4);  // slots per environment
     const int maxcon = std::min(32, 16 + 8 * nbox);  // two trips of 16 lanes
     const int hq = (16 * (nvp + 1) + 3) / 4;        // float4s of the 16 Hessian rows
-    int nj = 192;
+    // (a contact has at most nv entries: the Point's pool is 72 entries, not 192 - with ~150 KB of shared memory per block
+    // instead of 227 the SM keeps ~90 KB of L1, which is where the LOCAL arrays of the box-box narrow phase live; with the
+    // full carve-out they spill to L2 and the narrow phase, the critical path of the small robots' step, runs ~2x slower)
+    int nj = m.nv <= 4 ? std::min(192, round_up(maxcon * m.nv, 8)) : 192;
     for (; nj >= 48; nj -= 8) {
       L.es = nj + 2 * maxcon + hq;
       const int nat_bytes = (TE * L.es + 1) * 16;

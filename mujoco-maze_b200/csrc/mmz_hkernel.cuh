@@ -132,7 +132,10 @@ constexpr int HS = 33;  // row stride of the [slot][33] workspace
 __device__ unsigned long long g_phase[16];
 __device__ unsigned g_iter_hist[16];
 __device__ unsigned long long g_wsolve[16], g_wwait[16];  // per warp of block 0: its own solve, its wait for the slowest
-#define MMZ_TICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_phase[i] += t_ - tick_; tick_ = t_; } } while (0)
+__device__ unsigned long long g_wC[16], g_wD[16];  // per warp of block 0: its own work in phases C and D (before the barrier)
+__device__ unsigned g_launch;               // step launches so far
+__device__ unsigned g_blk[8];               // per-block phase cycles of this launch (thread 0 of every block; printed for launch MMZ_PRINT_LAUNCH)
+#define MMZ_TICK(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); if (blockIdx.x == 0) g_phase[i] += t_ - tick_; bphase[i] += (unsigned)(t_ - tick_); tick_ = t_; } } while (0)
 __device__ unsigned long long g_sec[16];  // solver sections, summed over the warps of block 0 (slot 15: Newton iterations)
 #define MMZ_STICK(i) do { if (blockIdx.x == 0 && e == 0) { const long long t_ = clock64(); atomicAdd(&g_sec[i], (unsigned long long)(t_ - stick_)); stick_ = t_; } } while (0)
 #else
@@ -161,6 +164,10 @@ struct HEnv {
   float4* jg;               // solver v2: this lane's environment in the Jacobian area, [contact][NVP + 1] float4
   float4* fg;               // solver v2: its per-contact (force, Hessian weights) pairs, [contact][2] float4
   float* hg;                // solver v3: this lane's row of the contact part of the Hessian, accumulated in shared memory
+#ifdef MMZ_PHASE_TIMING
+  unsigned bphase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int bmaxit = 0;
+#endif
   int e, wid;               // tree view: lane = environment e; warp wid takes items wid, wid + 16, ...
   int genv, lane, gshift;   // solver view: environment wid + 16 * (laneid / 16), lane = dof
   float limD[2], limA[2];   // this lane's joint-limit rows (solver view)
@@ -1629,6 +1636,7 @@ struct HEnv {
   MMZ_DI void forward(const TLayout& L, bool warmstart, int rk_stage = -1) {
 #ifdef MMZ_PHASE_TIMING
     long long tick_ = clock64();
+    if (threadIdx.x == 0) { bmaxit = 0; }
 #endif
     // A: the kinematic trees. Pass 0: pose and motion axes of the roots (and, on the idle warps, the joint-limit rows).
     // Pass 1: the roots' warps compute the roots' velocities (published through a named barrier), then their inertial forces; the subtree of every level-1 body is walked by a PAIR of warps: one runs pose +
@@ -1679,6 +1687,9 @@ struct HEnv {
     MMZ_TICK(2);
     // C: contact counting, mass matrix rows, smooth forces. Box candidate items keep their contacts for phase D.
     const int nit = n_items(L);
+#ifdef MMZ_PHASE_TIMING
+    const long long wc0_ = clock64();
+#endif
     constexpr int KEEP = BOX ? 3 : 1;
     BoxFound kept[KEEP];
     int nkept = 0;
@@ -1699,8 +1710,14 @@ struct HEnv {
         else smooth_dof(L, t - nit - L.nv);
       }
     }
+#ifdef MMZ_PHASE_TIMING
+    if (blockIdx.x == 0 && e == 0) g_wC[wid] += clock64() - wc0_;
+#endif
     __syncthreads();
     MMZ_TICK(3);
+#ifdef MMZ_PHASE_TIMING
+    const long long wd0_ = clock64();
+#endif
     // D: contacts into their slots (over the slots of arrays that are dead by now, see the layout): every warp writes
     // the items it counted - the kept box items as they are, the others through a second narrow phase
     if (!BOX) {
@@ -1719,6 +1736,9 @@ struct HEnv {
         }
       }
     }
+#ifdef MMZ_PHASE_TIMING
+    if (blockIdx.x == 0 && e == 0) g_wD[wid] += clock64() - wd0_;
+#endif
     if (wid == TW - 1) {
       int n = 0;
 #pragma unroll 1
@@ -1748,6 +1768,7 @@ struct HEnv {
     __syncthreads();
     if (blockIdx.x == 0 && e == 0) { g_wsolve[wid] += ts1_ - tick_; g_wwait[wid] += clock64() - ts1_; }
     MMZ_TICK(6);
+    if (threadIdx.x == 0) { int mx = 0; for (int k = 0; k < 32; k++) mx = max(mx, reinterpret_cast<int*>(sm)[(L.o_cnt + TN_ITER) * HS + k]); bphase[7] += mx; }
 #else
     __syncthreads();
 #endif

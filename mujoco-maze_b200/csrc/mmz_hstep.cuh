@@ -133,7 +133,18 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
     for (int i = 0; i < 16; i++) printf(" %llu/%llu", g_wsolve[i] / 1000, g_wwait[i] / 1000);
     printf("\n  solver sections (sum over the warps of block 0, kcycles): prologue %llu contact pass %llu gradient %llu hessian %llu elimination %llu rows %llu line search %llu update %llu | warp iterations %llu\n",
            g_sec[0] / 1000, g_sec[1] / 1000, g_sec[2] / 1000, g_sec[3] / 1000, g_sec[4] / 1000, g_sec[5] / 1000, g_sec[6] / 1000, g_sec[7] / 1000, g_sec[15]);
+    printf("  per warp C / D own work (kcycles):");
+    for (int i = 0; i < 16; i++) printf(" %llu/%llu", g_wC[i] / 1000, g_wD[i] / 1000);
+    printf("\n");
+    printf("  step (block 0, kcycles): prologue %llu mj_step %llu clamp / inner reward %llu reset + obs + rules %llu outputs %llu\n",
+           g_phase[8] / 1000, g_phase[9] / 1000, g_phase[10] / 1000, g_phase[11] / 1000, g_phase[12] / 1000);
   }
+#endif
+#ifdef MMZ_PHASE_TIMING
+  long long ktick_ = clock64();
+#define MMZ_KTICK(i) do { if (tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_phase[i] += t_ - ktick_; ktick_ = t_; } } while (0)
+#else
+#define MMZ_KTICK(i) do { } while (0)
 #endif
   HTask<NVP, BOX> T;
   T.m = reinterpret_cast<const mmz_model*>(smem);
@@ -211,8 +222,10 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
     }
     bool bad = T.state_bad(L);  // mj_checkPos / mj_checkVel of the incoming state
     __syncthreads();
+    MMZ_KTICK(8);  // prologue: model blob, state tile, actions, teleport
 #pragma unroll 1
     for (int k = 0; k < T.m->frame_skip; k++) bad = T.mj_step(L, bad);
+    MMZ_KTICK(9);  // mj_step x frame_skip
     float inner = 0.f, fwd = 0.f, cc = 0.f;
     bool moved = false;
     if (teleport) {
@@ -237,6 +250,7 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
       cc *= T.m->ctrl_cost_weight;
       inner = T.m->forward_reward_weight * fwd - cc;
     }
+    MMZ_KTICK(10);  // wall clamp / inner reward
     unsigned bits = bad ? T_UNSTABLE_BIT : 0;  // MuJoCo's mj_checkPos/Vel/Acc auto-reset: back to qpos0, zero velocity
     bool reset_now = bad, noise = false, refresh = bad || moved, live = true;
     float reward = 0.f, info0 = 0.f, info1 = 0.f;
@@ -272,6 +286,7 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
       }
     }
     __syncthreads();
+    MMZ_KTICK(11);  // reset / refresh / observation / task rules
     // ---- outputs: the block's observations are one contiguous chunk of obs[N][obs_dim]
     {
       const int nreal = min(TE, A.n - env0);
@@ -298,6 +313,15 @@ __global__ void __launch_bounds__(TW * 32, 1) maze_hkernel(const __grid_constant
       A.counters[env] = t;
       A.counters[A.npad + env] = nreset;
     }
+    MMZ_KTICK(12);  // outputs
+#ifdef MMZ_PHASE_TIMING
+    if (tid == 0) {
+      if (g_launch == 40)
+        printf("blk %d: rootkin %u walk %u B %u C %u D %u E %u solver %u | sum of max Newton iterations %u\n", (int)blockIdx.x,
+               T.bphase[0], T.bphase[1], T.bphase[2], T.bphase[3], T.bphase[4], T.bphase[5], T.bphase[6], T.bphase[7]);
+      if (blockIdx.x == 0) atomicAdd(&g_launch, 1u);
+    }
+#endif
   } else if (MODE == TMODE_FORWARD) {
     for (int a = wid; a < L.nu; a += TW)  // (the Point's motors are never driven: point.py:44-61)
       S(L.o_ctrl + a) = (real && T.m->step_kind != MMZ_STEP_TELEPORT) ? A.action[(size_t)env * L.nu + a] : 0.f;

@@ -128,29 +128,66 @@ MMZ_DI float capsule_nearest(const float* p0, const float* p1, const float* bc, 
 }
 
 // box against box: separating-axis search, then face clipping or an edge-edge point.
-// Normal from box A to box B; up to 8 contacts. Runs on a single lane (rare geoms: Point's
-// arrow box point.xml:22 and movable blocks), so it favours clarity over register use.
+// Normal from box A to box B; up to 8 contacts. This is the longest dependent chain of the small robots' step (the Point's
+// arrow box point.xml:22 against the maze boxes, movable blocks), so everything but the clipped polygon lives in REGISTERS:
+// the 15-axis search is fully unrolled (static row indices), rows picked at run time go through selects, the polygon
+// ping-pongs between two local arrays (one load per vertex and side). Local memory is slow here: with ~200 KB of shared
+// memory per block the SM has almost no L1 left and every local access is an L2 round trip.
+MMZ_DI void bb_row(const float (&M)[9], int i, float* r) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) r[k] = i == 0 ? M[k] : (i == 1 ? M[3 + k] : M[6 + k]);
+}
+MMZ_DI float bb_sel(const float* h, int i) { return i == 0 ? h[0] : (i == 1 ? h[1] : h[2]); }
+// one Sutherland-Hodgman pass: keep sg * (axs . (x - cr)) <= lim. Emits p if inside, then the crossing of (p, next)
+MMZ_DI int bb_clip(const float (*src)[3], int np, float (*dst)[3], const float* axs, float sg, float lim, const float* cr) {
+  constexpr int CAP = 12;
+  int nn = 0;
+  float p[3] = {src[0][0], src[0][1], src[0][2]};
+  float dp = sg * ((p[0] - cr[0]) * axs[0] + (p[1] - cr[1]) * axs[1] + (p[2] - cr[2]) * axs[2]) - lim;
+#pragma unroll 1
+  for (int i = 0; i < np; i++) {
+    const int in = i + 1 == np ? 0 : i + 1;
+    const float q[3] = {src[in][0], src[in][1], src[in][2]};
+    const float dq = sg * ((q[0] - cr[0]) * axs[0] + (q[1] - cr[1]) * axs[1] + (q[2] - cr[2]) * axs[2]) - lim;
+    if (dp <= 0.f && nn < CAP) { dst[nn][0] = p[0]; dst[nn][1] = p[1]; dst[nn][2] = p[2]; nn++; }
+    if ((dp <= 0.f) != (dq <= 0.f) && nn < CAP) {
+      const float t = dp / (dp - dq);
+#pragma unroll
+      for (int k = 0; k < 3; k++) dst[nn][k] = p[k] + t * (q[k] - p[k]);
+      nn++;
+    }
+    p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+    dp = dq;
+  }
+  return nn;
+}
 static __device__ __noinline__ int box_box(const float* ca, const float* Ra, const float* ha, const float* cb,
                                     const float* Rb, const float* hb, float margin, RawContact* out) {
-  float A[3][3], B[3][3], d[3];
+  float A[9], B[9], d[3];  // row i = axis i of the box in world coordinates
+#pragma unroll
   for (int i = 0; i < 3; i++)
-    for (int k = 0; k < 3; k++) { A[i][k] = Ra[3 * k + i]; B[i][k] = Rb[3 * k + i]; }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { A[3 * i + k] = Ra[3 * k + i]; B[3 * i + k] = Rb[3 * k + i]; }
+#pragma unroll
   for (int k = 0; k < 3; k++) d[k] = cb[k] - ca[k];
+  const float hav[3] = {ha[0], ha[1], ha[2]}, hbv[3] = {hb[0], hb[1], hb[2]};
   float best_f = -3.0e38f, best_e = -3.0e38f, nf[3] = {0, 0, 0}, ne[3] = {0, 0, 0};
   int code_f = -1, code_e = -1;
+#pragma unroll
   for (int code = 0; code < 15; code++) {
     float L[3];
-    if (code < 3) { L[0] = A[code][0]; L[1] = A[code][1]; L[2] = A[code][2]; }
-    else if (code < 6) { L[0] = B[code - 3][0]; L[1] = B[code - 3][1]; L[2] = B[code - 3][2]; }
+    if (code < 3) { L[0] = A[3 * code]; L[1] = A[3 * code + 1]; L[2] = A[3 * code + 2]; }
+    else if (code < 6) { L[0] = B[3 * (code - 3)]; L[1] = B[3 * (code - 3) + 1]; L[2] = B[3 * (code - 3) + 2]; }
     else {
-      cross3(L, A[(code - 6) / 3], B[(code - 6) % 3]);
+      cross3(L, A + 3 * ((code - 6) / 3), B + 3 * ((code - 6) % 3));
       float n = norm3(L);
       if (n < 1e-6f) continue;  // parallel edges: covered by the face axes
       float inv = 1.f / n;
       L[0] *= inv; L[1] *= inv; L[2] *= inv;
     }
     float ra = 0.f, rb = 0.f;
-    for (int i = 0; i < 3; i++) { ra += ha[i] * fabsf(dot3(L, A[i])); rb += hb[i] * fabsf(dot3(L, B[i])); }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { ra += hav[i] * fabsf(dot3(L, A + 3 * i)); rb += hbv[i] * fabsf(dot3(L, B + 3 * i)); }
     float dl = dot3(L, d);
     float s = fabsf(dl) - ra - rb;
     if (s > margin) return 0;
@@ -165,19 +202,33 @@ static __device__ __noinline__ int box_box(const float* ca, const float* Ra, con
   else { best = best_f; bcode = code_f; bn[0] = nf[0]; bn[1] = nf[1]; bn[2] = nf[2]; }
   if (bcode < 0) return 0;
   if (bcode >= 6) {  // edge-edge
-    int ia = (bcode - 6) / 3, ib = (bcode - 6) % 3;
+    const int ia = (bcode - 6) / 3, ib = (bcode - 6) % 3;
     float pa[3] = {ca[0], ca[1], ca[2]}, pb[3] = {cb[0], cb[1], cb[2]};
+#pragma unroll
     for (int i = 0; i < 3; i++) {
-      if (i != ia) { float sg = dot3(bn, A[i]) > 0.f ? 1.f : -1.f; for (int k = 0; k < 3; k++) pa[k] += sg * ha[i] * A[i][k]; }
-      if (i != ib) { float sg = dot3(bn, B[i]) > 0.f ? -1.f : 1.f; for (int k = 0; k < 3; k++) pb[k] += sg * hb[i] * B[i][k]; }
+      if (i != ia) {
+        float sg = dot3(bn, A + 3 * i) > 0.f ? 1.f : -1.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) pa[k] += sg * hav[i] * A[3 * i + k];
+      }
+      if (i != ib) {
+        float sg = dot3(bn, B + 3 * i) > 0.f ? -1.f : 1.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) pb[k] += sg * hbv[i] * B[3 * i + k];
+      }
     }
+    float Aia[3], Bib[3];
+    bb_row(A, ia, Aia);
+    bb_row(B, ib, Bib);
+    const float hia = bb_sel(hav, ia), hib = bb_sel(hbv, ib);
     float w[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]}, ua = 0.f, ub = 0.f;
-    float uaub = dot3(A[ia], B[ib]), q1 = dot3(A[ia], w), q2 = -dot3(B[ib], w), den = 1.f - uaub * uaub;
+    float uaub = dot3(Aia, Bib), q1 = dot3(Aia, w), q2 = -dot3(Bib, w), den = 1.f - uaub * uaub;
     if (den > 1e-9f) { ua = (q1 + uaub * q2) / den; ub = (uaub * q1 + q2) / den; }
-    ua = fminf(fmaxf(ua, -ha[ia]), ha[ia]);
-    ub = fminf(fmaxf(ub, -hb[ib]), hb[ib]);
+    ua = fminf(fmaxf(ua, -hia), hia);
+    ub = fminf(fmaxf(ub, -hib), hib);
+#pragma unroll
     for (int k = 0; k < 3; k++) {
-      float xa = pa[k] + ua * A[ia][k], xb = pb[k] + ub * B[ib][k];
+      float xa = pa[k] + ua * Aia[k], xb = pb[k] + ub * Bib[k];
       out->pos[k] = 0.5f * (xa + xb);
       out->normal[k] = bn[k];
       out->hint[k] = 0.f;
@@ -186,54 +237,55 @@ static __device__ __noinline__ int box_box(const float* ca, const float* Ra, con
     return 1;
   }
   // face contact: the reference box owns the axis, the incident box is the other
-  const float *cr, *hr, *ci, *hi;
-  float(*Rr)[3], (*Ri)[3];
-  float nr[3];
-  int ax;
-  if (bcode < 3) { cr = ca; hr = ha; Rr = A; ci = cb; hi = hb; Ri = B; ax = bcode; nr[0] = bn[0]; nr[1] = bn[1]; nr[2] = bn[2]; }
-  else { cr = cb; hr = hb; Rr = B; ci = ca; hi = ha; Ri = A; ax = bcode - 3; nr[0] = -bn[0]; nr[1] = -bn[1]; nr[2] = -bn[2]; }
+  const bool refa = bcode < 3;
+  const int ax = refa ? bcode : bcode - 3;
+  float Rr[9], Ri[9], cr[3], ci[3], hr[3], hi[3], nr[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) { Rr[k] = refa ? A[k] : B[k]; Ri[k] = refa ? B[k] : A[k]; }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    cr[k] = refa ? ca[k] : cb[k]; ci[k] = refa ? cb[k] : ca[k];
+    hr[k] = refa ? hav[k] : hbv[k]; hi[k] = refa ? hbv[k] : hav[k];
+    nr[k] = refa ? bn[k] : -bn[k];
+  }
   int iax = 0;
   float mind = 3.0e38f;
+#pragma unroll
   for (int i = 0; i < 3; i++) {
-    float v = fabsf(dot3(nr, Ri[i]));
+    float v = fabsf(dot3(nr, Ri + 3 * i));
     if (-v < mind) { mind = -v; iax = i; }
   }
-  float isg = dot3(nr, Ri[iax]) > 0.f ? -1.f : 1.f;
-  int u = (iax + 1) % 3, v = (iax + 2) % 3;
-  float poly[16][3], tmp[16][3];
-  int np = 4;
+  float Rix[3], Riu[3], Riv[3], Rru[3], Rrv[3];
+  const int u = (iax + 1) % 3, v = (iax + 2) % 3, ru = (ax + 1) % 3, rv = (ax + 2) % 3;
+  bb_row(Ri, iax, Rix); bb_row(Ri, u, Riu); bb_row(Ri, v, Riv);
+  bb_row(Rr, ru, Rru); bb_row(Rr, rv, Rrv);
+  const float hix = bb_sel(hi, iax), hiu = bb_sel(hi, u), hiv = bb_sel(hi, v);
+  const float hru = bb_sel(hr, ru), hrv = bb_sel(hr, rv), hrx = bb_sel(hr, ax);
+  const float isg = dot3(nr, Rix) > 0.f ? -1.f : 1.f;
+  float poly[12][3], tmp[12][3];
+#pragma unroll
   for (int c = 0; c < 4; c++) {
-    float su = (c == 0 || c == 3) ? -1.f : 1.f, sv = (c < 2) ? -1.f : 1.f;
-    for (int k = 0; k < 3; k++)
-      poly[c][k] = ci[k] + isg * hi[iax] * Ri[iax][k] + su * hi[u] * Ri[u][k] + sv * hi[v] * Ri[v][k];
+    const float su = (c == 0 || c == 3) ? -1.f : 1.f, sv = (c < 2) ? -1.f : 1.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) poly[c][k] = ci[k] + isg * hix * Rix[k] + su * hiu * Riu[k] + sv * hiv * Riv[k];
   }
-  int ru = (ax + 1) % 3, rv = (ax + 2) % 3;
-  for (int side = 0; side < 4; side++) {
-    const float* axs = Rr[side < 2 ? ru : rv];
-    float sg = (side & 1) ? -1.f : 1.f, lim = hr[side < 2 ? ru : rv];
-    int nn = 0;
-    for (int i = 0; i < np; i++) {
-      const float *p = poly[i], *q = poly[(i + 1) % np];
-      float rp[3] = {p[0] - cr[0], p[1] - cr[1], p[2] - cr[2]}, rq[3] = {q[0] - cr[0], q[1] - cr[1], q[2] - cr[2]};
-      float dp = sg * dot3(axs, rp) - lim, dq = sg * dot3(axs, rq) - lim;
-      if (dp <= 0.f) { tmp[nn][0] = p[0]; tmp[nn][1] = p[1]; tmp[nn][2] = p[2]; nn++; }
-      if ((dp <= 0.f) != (dq <= 0.f)) {
-        float t = dp / (dp - dq);
-        for (int k = 0; k < 3; k++) tmp[nn][k] = p[k] + t * (q[k] - p[k]);
-        nn++;
-      }
-    }
-    np = nn;
-    for (int i = 0; i < np; i++) { poly[i][0] = tmp[i][0]; poly[i][1] = tmp[i][1]; poly[i][2] = tmp[i][2]; }
-    if (np == 0) return 0;
-  }
+  int np = bb_clip(poly, 4, tmp, Rru, 1.f, hru, cr);
+  if (np == 0) return 0;
+  np = bb_clip(tmp, np, poly, Rru, -1.f, hru, cr);
+  if (np == 0) return 0;
+  np = bb_clip(poly, np, tmp, Rrv, 1.f, hrv, cr);
+  if (np == 0) return 0;
+  np = bb_clip(tmp, np, poly, Rrv, -1.f, hrv, cr);
+  if (np == 0) return 0;
   int n = 0;
+#pragma unroll 1
   for (int i = 0; i < np && n < 8; i++) {
-    float rp[3] = {poly[i][0] - cr[0], poly[i][1] - cr[1], poly[i][2] - cr[2]};
-    float depth = dot3(nr, rp) - hr[ax];
+    const float pp[3] = {poly[i][0], poly[i][1], poly[i][2]};
+    const float depth = (pp[0] - cr[0]) * nr[0] + (pp[1] - cr[1]) * nr[1] + (pp[2] - cr[2]) * nr[2] - hrx;
     if (depth >= margin) continue;
+#pragma unroll
     for (int k = 0; k < 3; k++) {
-      out[n].pos[k] = poly[i][k] - nr[k] * depth * 0.5f;
+      out[n].pos[k] = pp[k] - nr[k] * depth * 0.5f;
       out[n].normal[k] = bn[k];
       out[n].hint[k] = 0.f;
     }
