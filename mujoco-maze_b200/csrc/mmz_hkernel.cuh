@@ -151,7 +151,12 @@ __device__ unsigned long long g_sec[16];  // solver sections, summed over the wa
 enum { K_POS = 0, K_N = 3, K_T1 = 6, K_BODY1 = 9, K_BODY2 = 10, K_MPOS = 9, K_MNEG = 10, K_MU = 11, K_D = 12, K_AREF = 13,
        K_DIST = 13, K_INVW = 14, K_GEOM = 15, K_OTHER = 16, K_JAR = 0, K_STRIDE = 17,
        K3_JV = 4, K3_JOFF = 17, K3_STRIDE = 19 };  // solver v3: J dir per pyramid row (over the dead point / normal), offset of the contact's Jacobian entries
+// (Without box geoms the narrow-phase result travels BY VALUE, in registers: a RawContact passed by reference lives in local
+// memory, and with the whole shared memory in use the SM has no L1 left - every local access is an L2 round trip: AntUMaze
+// 6.05 -> 5.96 ms. The box instances keep their contacts in local arrays anyway and are faster by reference - measured.)
 static __device__ __noinline__ void write_contact_record2(float* c, const RawContact& rc, int b1, int b2, float iw, int g, int other);
+static __device__ __noinline__ void write_contact_record2v(float* c, float dist, float px, float py, float pz, float nx, float ny, float nz,
+                                                          float hx, float hy, float hz, int b1, int b2, float iw, int g, int other);
 
 
 template <int NVP, int BOX>
@@ -505,7 +510,10 @@ struct HEnv {
   // stores a narrow-phase record into contact slot `slot` (layout K_* above); the normal points
   // from body b1 (geom1) to body b2 (geom2), -1 = world
   MMZ_DI void write_contact(const TLayout& L, int slot, const RawContact& rc, int b1, int b2, float iw, int g, int other) {
-    write_contact_record2(sm + (L.o_con + slot * L.cstride) * HS + e, rc, b1, b2, iw, g, other);
+    float* c = sm + (L.o_con + slot * L.cstride) * HS + e;
+    if constexpr (BOX != 0) write_contact_record2(c, rc, b1, b2, iw, g, other);
+    else write_contact_record2v(c, rc.dist, rc.pos[0], rc.pos[1], rc.pos[2], rc.normal[0], rc.normal[1], rc.normal[2], rc.hint[0], rc.hint[1],
+                                rc.hint[2], b1, b2, iw, g, other);
   }
   // number of collision items: one per geom, then (BOX only) BCAND candidate slots per box geom
   static constexpr int BCELLS = 9;                       // maze cells a box geom can reach (3 x 3)
@@ -642,6 +650,7 @@ struct HEnv {
               for (int k = 0; k < 3; k++) { rc.pos[k] = end == 0 ? p0[k] : p1[k]; rc.normal[k] = (k == 2) ? 1.f : 0.f; rc.hint[k] = hint[k]; }
               rc.dist = d; rc.pos[2] -= r + 0.5f * d;
               write_contact(L, base + n, rc, -1, body, invw, g, -1);
+              if (kRowsInD) contact_rows2(L, base + n);
             }
             n++;
           }
@@ -695,8 +704,8 @@ struct HEnv {
               n1 = 0;
             }
           }
-          if (n0) { hits |= cbit; if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r0, body, b2, iw, g, other); n++; }
-          if (n1) { hits |= cand < 12 ? cbit << 1 : cbit; if (pass == 1 && base + n < L.maxcon) write_contact(L, base + n, r1, body, b2, iw, g, other); n++; }
+          if (n0) { hits |= cbit; if (pass == 1 && base + n < L.maxcon) { write_contact(L, base + n, r0, body, b2, iw, g, other); if (kRowsInD) contact_rows2(L, base + n); } n++; }
+          if (n1) { hits |= cand < 12 ? cbit << 1 : cbit; if (pass == 1 && base + n < L.maxcon) { write_contact(L, base + n, r1, body, b2, iw, g, other); if (kRowsInD) contact_rows2(L, base + n); } n++; }
         }
       }
     } else if (BOX) {
@@ -737,8 +746,11 @@ struct HEnv {
   // contact slot c (tree view): narrow-phase record -> D, aref[4], signed dof masks, point relative to the
   // reference. J qvel is the point velocity of body2 minus body1, from the body velocities RNE has computed.
   // the same for the record of solver v2
+  // Without box geoms (an item has one or two contacts) the warp that wrote a record computes its rows right away: no
+  // barrier and no separate phase for the rows (AntUMaze 5.955 -> 5.926 ms). With box geoms an item can have 8 contacts
+  // and the rows are spread over the warps in their own phase E (merged: PointUMaze 0.164 -> 0.175 ms, AntPush 6.41 -> 6.69).
+  static constexpr bool kRowsInD = BOX == 0;
   MMZ_DI void contact_rows2(const TLayout& L, int c) {
-    if (c >= I(L.o_cnt + TN_CON)) return;
     const int o = L.o_con + c * L.cstride;
     float rf[3], cp[3], fr[9], par[9], v[3] = {0.f, 0.f, 0.f};
     ref(L, rf);
@@ -951,28 +963,28 @@ struct HEnv {
   }
   // Newton solver (mj_solNewton), same algorithm and stopping rules as solve_g
   MMZ_DI void solve_g2(const TLayout& L, bool warmstart) {
-    const int nv = L.nv, ncon = IW(L.o_cnt + TN_CON);
+    const int nv = L.nv;
 #ifdef MMZ_PHASE_TIMING
     long long stick_ = clock64();
 #endif
-    const int ncw = max(ncon, __shfl_xor_sync(kAll, ncon, 16));  // the two environments of the warp
     const bool me = lane < nv;
     const unsigned limbits = gballot(limD[0] > 0.f || limD[1] > 0.f);
-    const bool constrained = ncon > 0 || limbits != 0;
     float mrow[NVP];  // this lane's row of the mass matrix (zero outside its sparsity pattern and outside the model)
     const int rel = me ? dv->dof_rel[lane] : 0;
 #pragma unroll
     for (int k = 0; k < NVP; k++) mrow[k] = (rel >> k & 1) ? W_(L.o_M + lane * L.ldm + k) : 0.f;
     const float sm_ = me ? W_(L.o_smooth + lane) : 0.f;
-    {
-      float cd[6];
+    float cd[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) cd[k] = me ? W_(L.o_cdof + 6 * lane + k) : 0.f;
-      // The Jacobian area overlays the mass matrix, the motion axes and every other array the solver view has read by
-      // now (all environments of the block, in the other layout): no warp may write it before all warps are here.
-      __syncthreads();
-      build_jac(L, cd, ncon, ncw);
-    }
+    for (int k = 0; k < 6; k++) cd[k] = me ? W_(L.o_cdof + 6 * lane + k) : 0.f;
+    // The Jacobian area overlays the mass matrix, the motion axes and every other array the solver view has read by
+    // now (all environments of the block, in the other layout): no warp may write it before all warps are here. The
+    // same barrier ends phase D (contact records, their rows, the contact count).
+    __syncthreads();
+    const int ncon = IW(L.o_cnt + TN_CON);
+    const int ncw = max(ncon, __shfl_xor_sync(kAll, ncon, 16));  // the two environments of the warp
+    const bool constrained = ncon > 0 || limbits != 0;
+    build_jac(L, cd, ncon, ncw);
     float al = (warmstart && me) ? W_(L.o_qacc + lane) : 0.f;
     if (!(fabsf(al) < kMaxVal)) al = 0.f;  // a blown-up environment restarts from zero
     if (me) W_(L.o_qacc + lane) = al;
@@ -1746,18 +1758,20 @@ struct HEnv {
       if (n > L.maxcon) I(L.o_cnt + TN_OVERFLOW) = 1;
       I(L.o_cnt + TN_CON) = min(n, L.maxcon);
     }
-    __syncthreads();
-    MMZ_TICK(4);
-    // E: contact rows
-    {
+    if (kRowsInD) {
+      // No barrier here: the contact rows were computed by the warps that wrote the records. The solver view first loads
+      // its registers - mass matrix, smooth forces, motion axes, all complete since the barrier that ended phase C - and
+      // then passes ITS block barrier before it reads the contact count and the records or touches the Jacobian area.
+      MMZ_TICK(4);
+    } else {
+      __syncthreads();
+      MMZ_TICK(4);
+      // E: contact rows (the solver's own block barrier orders them against their readers)
       const int ncmax = __reduce_max_sync(kAll, I(L.o_cnt + TN_CON));
-      for (int c = wid; c < ncmax; c += TW) {
-        contact_rows2(L, c);
-      }
+      for (int c = wid; c < ncmax; c += TW)
+        if (c < I(L.o_cnt + TN_CON)) contact_rows2(L, c);
+      MMZ_TICK(5);
     }
-    // (solver v2 loads its registers first and has its own block barrier before it touches the Jacobian area: that one
-    // also orders the contact rows above against their readers)
-    MMZ_TICK(5);
     // solver view: warp w owns environments w and w + 16
     limit_rows_g(L);
     if (V2) solve_g2(L, warmstart);
@@ -1823,6 +1837,20 @@ static __device__ __noinline__ void write_contact_record2(float* c, const RawCon
 #pragma unroll
   for (int k = 0; k < 6; k++) c[(K_N + k) * HS] = fr[k];
   c[K_DIST * HS] = rc.dist;
+  c[K_INVW * HS] = iw;
+  c[K_BODY1 * HS] = __int_as_float(b1);
+  c[K_BODY2 * HS] = __int_as_float(b2);
+  c[K_GEOM * HS] = __int_as_float(g);
+  c[K_OTHER * HS] = __int_as_float(other);
+}
+static __device__ __noinline__ void write_contact_record2v(float* c, float dist, float px, float py, float pz, float nx, float ny, float nz,
+                                                           float hx, float hy, float hz, int b1, int b2, float iw, int g, int other) {
+  float fr[9] = {nx, ny, nz, hx, hy, hz, 0.f, 0.f, 0.f};
+  make_frame(fr);
+  c[(K_POS + 0) * HS] = px; c[(K_POS + 1) * HS] = py; c[(K_POS + 2) * HS] = pz;
+#pragma unroll
+  for (int k = 0; k < 6; k++) c[(K_N + k) * HS] = fr[k];
+  c[K_DIST * HS] = dist;
   c[K_INVW * HS] = iw;
   c[K_BODY1 * HS] = __int_as_float(b1);
   c[K_BODY2 * HS] = __int_as_float(b2);
