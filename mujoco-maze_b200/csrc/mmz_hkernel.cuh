@@ -599,10 +599,31 @@ struct HEnv {
     }
     f.n = n;
   }
+  // (all contacts of one box item share their normal - the clipped face's, the floor's - hence their frame: made once)
   MMZ_DI void box_item_write(const TLayout& L, int item, int base, const BoxFound& f) {
+    const int nw = __reduce_max_sync(kAll, f.n);
+    if (nw == 0) return;
+    float fr[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { fr[k] = f.n > 0 ? f.rc[0].normal[k] : (k == 2 ? 1.f : 0.f); fr[3 + k] = f.n > 0 ? f.rc[0].hint[k] : 0.f; }
+    make_frame(fr);
 #pragma unroll 1
-    for (int k = 0; k < f.n; k++)
-      if (base + k < L.maxcon) write_contact(L, base + k, f.rc[k], f.b1, f.b2, f.iw, f.g, f.other);
+    for (int k = 0; k < nw; k++) {
+      if (k < f.n && base + k < L.maxcon) {
+        float* c = sm + (L.o_con + (base + k) * L.cstride) * HS + e;
+        const RawContact& rc = f.rc[k];
+#pragma unroll
+        for (int i = 0; i < 3; i++) c[(K_POS + i) * HS] = rc.pos[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) c[(K_N + i) * HS] = fr[i];
+        c[K_DIST * HS] = rc.dist;
+        c[K_INVW * HS] = f.iw;
+        c[K_BODY1 * HS] = __int_as_float(f.b1);
+        c[K_BODY2 * HS] = __int_as_float(f.b2);
+        c[K_GEOM * HS] = __int_as_float(f.g);
+        c[K_OTHER * HS] = __int_as_float(f.other);
+      }
+    }
   }
   // Collision item `item`. pass 0 counts its contacts (into o_gcnt), pass 1 writes them at the slots following those
   // of the items before it: the contact order is the item order, independent of warp timing.
