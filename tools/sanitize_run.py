@@ -28,6 +28,12 @@ for k in range(steps):
     a = lo + (hi - lo) * torch.rand((n, lo.numel()), device="cuda:0", generator=g)
     obs, rew, done, info = env.step(a)
     ndone += int((done.to(torch.uint8) & 1).sum().item()) if torch.is_tensor(done) else int(np.sum(done))
+# the host call: pinned buffers mapped into the device address space, read / written by the step kernel itself
+h = [torch.empty(s, dtype=d).pin_memory() for s, d in (((n, sim.nu), torch.float32), ((n, sim.obs_dim), torch.float32),
+                                                       ((n,), torch.float32), ((n,), torch.uint8), ((n, 4), torch.float32))]
+h[0].copy_(a.cpu())
+sim.step_host(*h)
+assert bool(torch.isfinite(h[1]).all())
 torch.cuda.synchronize()
 print(f"{env_id}: {sim.kernel_config['kernel']} x{n}, {steps} steps, {ndone} episode ends (auto-reset), obs finite: "
       f"{bool(torch.isfinite(obs).all())}")
