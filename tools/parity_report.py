@@ -24,7 +24,7 @@ out = [
     "",
     "Comparator: the fp64 CPU restatement `oracle/mmz_oracle.c` (physics parity-UNPINNED against MuJoCo, see DESIGN.md section 4); "
     "clamp and top-down-view goldens: the REAL reference Python code. Model convention of every run: `legacy_capsule_volume=True` "
-    "(MuJoCo 2.0 capsule volume pi r^2 L + pi r^3, pinned by tests/test_abi_and_host.py), welded bodies merged, line-search tolerance 1e-3.",
+    "(MuJoCo 2.0 capsule volume pi r^2 L + pi r^3, pinned by tests/test_abi_and_host.py), welded bodies merged, line-search tolerance 1e-2 (MuJoCo's default ls_tolerance).",
     "Teacher-forced single evaluations / steps from identical (qpos, qvel, t, action); relative errors are |gpu - oracle| / (1 + |oracle|). "
     f"{ntests} GPU tests, all green (last run of the round, final kernels; regenerate with `python tools/parity_report.py`).",
     "",
