@@ -1298,7 +1298,8 @@ struct HEnv {
   }
   // lane = contact (16 per trip): J x over the dofs of the contact's mask. which 0: x = qacc -> J a - aref, force and
   // Hessian weights of the active rows; which 1: x = direction -> J dir per pyramid row into the record
-  MMZ_DI void contact_pass3(const TLayout& L, int xoff, int ncon, int ncw, int which) {
+  // (which 1: the rows of the first 16 contacts stay in the lane, `jvreg`, for the line search; later ones go to the records)
+  MMZ_DI void contact_pass3(const TLayout& L, int xoff, int ncon, int ncw, int which, float* jvreg = nullptr) {
 #pragma unroll 1
     for (int t0 = 0; t0 < ncw; t0 += 16) {
       const int c = t0 + lane;
@@ -1333,7 +1334,8 @@ struct HEnv {
           if (two) { s0 = fmaf(j1.x, x1, s0); s1 = fmaf(j1.y, x1, s1); s2 = fmaf(j1.z, x1, s2); sa = fmaf(j1.w, fabsf(x1), sa); }
         }
         if (which == 1) {
-          W_(cs + K3_JV) = s0 + s1; W_(cs + K3_JV + 1) = s0 - s1; W_(cs + K3_JV + 2) = s0 + s2; W_(cs + K3_JV + 3) = s0 - s2;
+          if (t0 == 0) { jvreg[0] = s0 + s1; jvreg[1] = s0 - s1; jvreg[2] = s0 + s2; jvreg[3] = s0 - s2; }
+          else { W_(cs + K3_JV) = s0 + s1; W_(cs + K3_JV + 1) = s0 - s1; W_(cs + K3_JV + 2) = s0 + s2; W_(cs + K3_JV + 3) = s0 - s2; }
           continue;
         }
         const float r0 = W_(cs + K_AREF), r1 = W_(cs + K_AREF + 1), r2 = W_(cs + K_AREF + 2), r3 = W_(cs + K_AREF + 3);
@@ -1351,9 +1353,18 @@ struct HEnv {
   }
   // derivative and curvature of the cost along the direction from the rows of this lane: its two joint-limit rows
   // (registers) and the pyramid rows r = lane, lane + 16, ... of the contacts (records); `fl`: a row changed sides
-  MMZ_DI void ls_rows3(const TLayout& L, int ncon, const float (&ljar)[2], float dr, float alpha, float* g, float* h, bool* fl) const {
+  // The four pyramid rows of contact `lane` (the first 16 contacts) come from registers: (rj, rv, rD) = (J a - aref, J dir, D),
+  // (1, 0, 0) for a lane without a contact.
+  MMZ_DI void ls_rows3(const TLayout& L, int ncon, const float (&ljar)[2], float dr, float alpha, const float (&rj)[4],
+                       const float (&rv)[4], float rD, float* g, float* h, bool* fl) const {
     float gg = 0.f, hh = 0.f;
     bool f = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float x = rj[i] + alpha * rv[i];
+      if (x < 0.f) { gg += rD * x * rv[i]; hh += rD * rv[i] * rv[i]; }
+      f |= (x < 0.f) != (rj[i] < 0.f);
+    }
 #pragma unroll
     for (int s = 0; s < 2; s++) {
       const float jv = s == 0 ? dr : -dr, x = ljar[s] + alpha * jv;
@@ -1361,7 +1372,7 @@ struct HEnv {
       f |= limD[s] > 0.f && (x < 0.f) != (ljar[s] < 0.f);
     }
 #pragma unroll 1
-    for (int r = lane; r < 4 * ncon; r += 16) {
+    for (int r = 64 + lane; r < 4 * ncon; r += 16) {
       const int cs = L.o_con + (r >> 2) * L.cstride;
       const float jv = W_(cs + K3_JV + (r & 3)), jar = W_(cs + K_JAR + (r & 3)), x = jar + alpha * jv, D = W_(cs + K_D);
       if (x < 0.f) { gg += D * x * jv; hh += D * jv * jv; }
@@ -1539,14 +1550,21 @@ struct HEnv {
 #pragma unroll
       for (int k = 0; k < NVP; k++) { const float t = mrow[k] * W_(L.o_dir + k); md += t; mdabs += fabsf(t); }
       if (__any_sync(kAll, constrained && !done)) {
-        contact_pass3(L, L.o_dir, done ? 0 : ncon, ncw, 1);
-        __syncwarp();
         const int nls = done ? 0 : ncon;
+        float rj[4] = {1.f, 1.f, 1.f, 1.f}, rv[4] = {0.f, 0.f, 0.f, 0.f}, rD = 0.f;
+        contact_pass3(L, L.o_dir, nls, ncw, 1, rv);
+        if (lane < nls) {
+          const int cs = L.o_con + lane * L.cstride;
+#pragma unroll
+          for (int i = 0; i < 4; i++) rj[i] = W_(cs + K_JAR + i);
+          rD = W_(cs + K_D);
+        }
+        __syncwarp();
         bool lsdone = done || !constrained;
         bool flipped = false, lsconv = false;  // did a row change sides between 0 and alpha; did the search converge
         float g, h;
         bool fl;
-        ls_rows3(L, nls, ljar, dr, 1.f, &g, &h, &fl);
+        ls_rows3(L, nls, ljar, dr, 1.f, rj, rv, rD, &g, &h, &fl);
         // the full Newton step crosses no row: it is the minimiser along the direction, no search needed
         flipped = gballot(fl) != 0;
         if (!flipped && !lsdone) { lsdone = true; lsconv = true; }
@@ -1557,7 +1575,7 @@ struct HEnv {
           float lo = 0.f, hi = -1.f;
 #pragma unroll 1
           for (int k = 0; k < kTMaxLineSearch; k++) {
-            if (k > 0) ls_rows3(L, nls, ljar, dr, alpha, &g, &h, &fl);
+            if (k > 0) ls_rows3(L, nls, ljar, dr, alpha, rj, rv, rD, &g, &h, &fl);
             g = gsum16(g) + g0 + alpha * h0;
             h = gsum16(h) + h0;
             if (!lsdone) {
@@ -1573,7 +1591,7 @@ struct HEnv {
             }
             if (__all_sync(kAll, lsdone)) break;
           }
-          ls_rows3(L, nls, ljar, dr, alpha, &g, &h, &fl);  // sides at the accepted step against those at 0
+          ls_rows3(L, nls, ljar, dr, alpha, rj, rv, rD, &g, &h, &fl);  // sides at the accepted step against those at 0
           const bool any = gballot(fl) != 0;
           if (searched) flipped = any;
         }
