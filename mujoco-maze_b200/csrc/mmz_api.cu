@@ -514,6 +514,19 @@ void make_tderived(const mmz_model& m, TDerived* d) {
         if (m.body_parent[c] == b && !(m.body_jntnum[c] == 1 && m.jnt_type[m.body_jntadr[c]] == MMZ_JNT_HINGE)) fast = false;
       if (getenv("MMZ_NO_FAST_KIN")) fast = false;  // development aid
       d->kin_fast[b] = fast ? 1 : 0;
+      {  // 2: a root body without rotation on slide x, slide y, hinge z through its origin (the Point)
+        const int j = m.body_jntadr[b];
+        auto is = [&](int jj, int type, int axis) {
+          for (int k = 0; k < 3; k++)
+            if (m.jnt_axis[jj][k] != (k == axis ? 1.f : 0.f) || m.jnt_pos[jj][k] != 0.f) return false;
+          return m.jnt_type[jj] == type;
+        };
+        const bool planar = m.body_parent[b] < 0 && m.body_jntnum[b] == 3 && m.body_quat[b][0] == 1.f && m.body_quat[b][1] == 0.f &&
+                            m.body_quat[b][2] == 0.f && m.body_quat[b][3] == 0.f && is(j, MMZ_JNT_SLIDE, 0) && is(j + 1, MMZ_JNT_SLIDE, 1) &&
+                            is(j + 2, MMZ_JNT_HINGE, 2) && m.jnt_qadr[j + 1] == m.jnt_qadr[j] + 1 && m.jnt_qadr[j + 2] == m.jnt_qadr[j] + 2 &&
+                            m.jnt_dadr[j + 1] == m.jnt_dadr[j] + 1 && m.jnt_dadr[j + 2] == m.jnt_dadr[j] + 2;
+        if (planar && !getenv("MMZ_NO_FAST_KIN")) d->kin_fast[b] = 2;
+      }
       if (!fast) continue;
       const int j = m.body_jntadr[b];
       float* Rb = d->kin_Rb[b];

@@ -194,7 +194,7 @@ struct HEnv {
     const int p = m->body_parent[b];
     float pos[3], quat[4], R[9], rf[3];
     ref(L, rf);
-    if (dv->kin_fast[b]) {  // one hinge below a moving body: matrices only (TDerived::kin_*)
+    if (dv->kin_fast[b] == 1) {  // one hinge below a moving body: matrices only (TDerived::kin_*)
       const int j = m->body_jntadr[b], qa = m->jnt_qadr[j], d = m->jnt_dadr[j];
       float sn, cs;
       __sincosf(S(L.o_qpos + qa) - m->qpos0[qa], &sn, &cs);
@@ -231,6 +231,27 @@ struct HEnv {
       for (int k = 0; k < 9; k++) S(L.o_xmat + 9 * b + k) = R[k];
       return;
     }
+    int freed = -1;  // first dof of a free joint of this body
+    if (BOX != 0 && dv->kin_fast[b] == 2) {  // (compiled into the box instances only: the Point always carries its arrow box)
+      // The Point (point.xml:19-26): a root body on slide x, slide y and a hinge about z, all through its origin, no body
+      // rotation. The generic joint loop below does three quat2mat, a quaternion product and a dozen dependent loads of
+      // joint constants for what is a translation and one rotation about z - and this body is the whole tree walk of the
+      // small robots: their step waits for this one warp.
+      const int j = m->body_jntadr[b], qa = m->jnt_qadr[j], d = m->jnt_dadr[j];
+      const float x = S(L.o_qpos + qa) - m->qpos0[qa], y = S(L.o_qpos + qa + 1) - m->qpos0[qa + 1];
+      const float th = S(L.o_qpos + qa + 2) - m->qpos0[qa + 2];
+      pos[0] = m->body_pos[b][0] + x; pos[1] = m->body_pos[b][1] + y; pos[2] = m->body_pos[b][2];
+      const float zax[3] = {0.f, 0.f, 1.f};
+      axisangle2quat(quat, zax, th);
+      const float at[2] = {pos[0] - rf[0], pos[1] - rf[1]};
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        S(L.o_cdof + 6 * d + i) = i == 3 ? 1.f : 0.f;
+        S(L.o_cdof + 6 * (d + 1) + i) = i == 4 ? 1.f : 0.f;
+      }
+      S(L.o_cdof + 6 * (d + 2) + 0) = 0.f; S(L.o_cdof + 6 * (d + 2) + 1) = 0.f; S(L.o_cdof + 6 * (d + 2) + 2) = 1.f;
+      S(L.o_cdof + 6 * (d + 2) + 3) = at[1]; S(L.o_cdof + 6 * (d + 2) + 4) = -at[0]; S(L.o_cdof + 6 * (d + 2) + 5) = 0.f;
+    } else {
     if (p < 0) {
 #pragma unroll
       for (int k = 0; k < 3; k++) pos[k] = m->body_pos[b][k];
@@ -248,7 +269,6 @@ struct HEnv {
       quat_mul(quat, qp, m->body_quat[b]);
     }
     const int j0 = m->body_jntadr[b], j1 = j0 + m->body_jntnum[b];
-    int freed = -1;  // first dof of a free joint of this body
 #pragma unroll 1
     for (int j = j0; j < j1; j++) {
       const int qa = m->jnt_qadr[j], type = m->jnt_type[j], d = m->jnt_dadr[j];
@@ -292,6 +312,7 @@ struct HEnv {
       }
 #pragma unroll
       for (int i = 0; i < 6; i++) S(L.o_cdof + 6 * d + i) = c[i];
+    }
     }
     quat_norm(quat);
     quat2mat(R, quat);
