@@ -150,7 +150,7 @@ __device__ unsigned long long g_sec[16];  // solver sections, summed over the wa
 // frame are dead and J a - aref of the four pyramid rows takes their place.
 enum { K_POS = 0, K_N = 3, K_T1 = 6, K_BODY1 = 9, K_BODY2 = 10, K_MPOS = 9, K_MNEG = 10, K_MU = 11, K_D = 12, K_AREF = 13,
        K_DIST = 13, K_INVW = 14, K_GEOM = 15, K_OTHER = 16, K_JAR = 0, K_STRIDE = 17,
-       K3_JV = 4, K3_JOFF = 17, K3_STRIDE = 19 };  // solver v3: J dir per pyramid row (over the dead point / normal), offset of the contact's Jacobian entries
+       K3_JV = 4, K3_JOFF = 17, K3_STRIDE = 19 };  // solver v3: J dir per pyramid row of contacts 16.. (over the dead point / normal); ONE word: the contact's dof mask | offset of its Jacobian entries << 16
 // (Without box geoms the narrow-phase result travels BY VALUE, in registers: a RawContact passed by reference lives in local
 // memory, and with the whole shared memory in use the SM has no L1 left - every local access is an L2 round trip: AntUMaze
 // 6.05 -> 5.96 ms. The box instances keep their contacts in local arrays anyway and are faster by reference - measured.)
