@@ -143,6 +143,57 @@ def test_forward_parity(env_id, torch_cuda, oracle_lib):
     assert np.median(rel) < 1e-4, stats
 
 
+def test_forward_parity_ant_against_block(torch_cuda, oracle_lib):
+    """AntPush-v0 with the ants pressed against the movable block (maze_env.py:563-660): contacts that move dofs of BOTH
+    dof trees couple them in the Hessian, so solver v3 must leave its side-by-side elimination of the two trees and its
+    lane = contact passes for block-only contacts must coexist with Ant-block contacts in the per-contact loops."""
+    from mujoco_maze.backend import BatchedSim
+
+    torch = torch_cuda
+    env_id = "AntPush-v0"
+    rng = np.random.default_rng(31)
+    model = make_model(env_id)
+    n = 192
+    q, v = sample_states(model, env_id, n, rng)
+    block = np.asarray(model.body_pos, float)[int(model.nbody) - 1]
+    half = np.asarray(model.geom_size, float)[int(model.ngeom) - 1]
+    q[:, 15:17] = rng.uniform(-0.05, 0.05, size=(n, 2))
+    q[:, 0] = block[0] + rng.uniform(-0.5 * half[0], 0.5 * half[0], size=n)
+    q[:, 1] = block[1] - half[1] - rng.uniform(0.35, 0.9, size=n)  # torso 0.35 .. 0.9 in front of the block's face
+    a = sample_actions(model, n, rng)
+    sim = BatchedSim(model, n)
+    sim.set_state(q, v, np.zeros(n, dtype=np.int32))
+    qacc, diag = sim.forward(a)
+    torch.cuda.synchronize()
+    qacc, diag = qacc.cpu().numpy().astype(np.float64), diag.cpu().numpy()
+    o = oracle_lib.OracleEnv(model)
+    ref = np.zeros_like(qacc)
+    cnt, far = np.zeros((n, 2), dtype=np.int64), np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        o.set_state(q[i], v[i])
+        ref[i] = o.forward(a[i])
+        c = o.counts()
+        cnt[i] = [c["ncon"], c["nefc"]]
+        qf = q[i].copy()
+        qf[1] -= 3.0  # the same pose away from the block: what is left are floor contacts
+        o.set_state(qf, v[i])
+        o.forward(a[i])
+        far[i] = o.counts()["ncon"]
+    touching = cnt[:, 0] > far
+    same_rows = (diag[:, 0] == cnt[:, 0]) & (diag[:, 1] == cnt[:, 1])
+    rel = (np.abs(qacc - ref) / (1.0 + np.abs(ref).max(axis=1, keepdims=True))).max(axis=1)
+    stats = dict(env=env_id, n=n, touching=float(touching.mean()), frac_same_rows=float(same_rows.mean()),
+                 max_rel_err_same_rows=float(rel[same_rows].max()), median_rel_err=float(np.median(rel)),
+                 ncon_mean=float(cnt[:, 0].mean()), ncon_max=int(cnt[:, 0].max()), kernel=sim.kernel_config)
+    _dump("forward_ant_against_block", stats)
+    print(stats)
+    assert touching.mean() > 0.5, stats  # the premise of the test: most ants touch the block
+    assert diag[:, 3].sum() == 0, "contact buffer overflow"
+    assert same_rows.mean() >= 0.97 and np.isfinite(qacc).all()
+    assert rel[same_rows].max() < 2e-3, stats
+    assert np.median(rel) < 1e-4, stats
+
+
 @pytest.mark.parametrize("env_id", ENV_IDS)
 def test_step_parity(env_id, torch_cuda, oracle_lib):
     """One MazeEnv.step from identical state and action: obs (qpos, qvel, object positions, time), reward, done, info."""
