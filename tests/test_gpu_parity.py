@@ -185,7 +185,7 @@ def test_forward_parity_ant_against_block(torch_cuda, oracle_lib):
     stats = dict(env=env_id, n=n, touching=float(touching.mean()), frac_same_rows=float(same_rows.mean()),
                  max_rel_err_same_rows=float(rel[same_rows].max()), median_rel_err=float(np.median(rel)),
                  ncon_mean=float(cnt[:, 0].mean()), ncon_max=int(cnt[:, 0].max()), kernel=sim.kernel_config)
-    _dump("forward_ant_against_block", stats)
+    _dump("coupled_AntPush-v0", stats)
     print(stats)
     assert touching.mean() > 0.5, stats  # the premise of the test: most ants touch the block
     assert diag[:, 3].sum() == 0, "contact buffer overflow"
