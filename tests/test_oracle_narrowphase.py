@@ -1,0 +1,134 @@
+"""Known answers for the narrow phase of the CPU restatement (oracle/mmz_oracle.c:400-647) in configurations whose contacts
+follow from elementary geometry - the cases in which any correct narrow phase, MuJoCo's mjc_PlaneSphere / mjc_SphereBox /
+mjc_BoxBox included, must produce the same points: distance negative by the penetration, position midway between the two
+surfaces, normal from geom 1 to geom 2 (the conventions of mmz_narrow.cuh:1-8). Geometry of the scenes: the Point of
+assets/point.xml (sphere r = 0.5 at z = 0.5, arrow box 0.5 x 0.1 x 0.1 at 0.6 ahead) in the U maze of maze_task.py (cells of
+4, walls 2 high: the cell west of the start cell is a wall whose east face is the plane x = -2), the Ant's torso sphere
+(r = 0.25) over the floor."""
+import numpy as np
+import pytest
+
+from conftest import make_model
+
+
+@pytest.fixture(scope="module")
+def point(oracle_lib):
+    model = make_model("PointUMaze-v0")
+    assert float(model.cell_size) == 4.0 and np.allclose(np.asarray(model.wall_half), [2, 2, 1])
+    return oracle_lib.OracleEnv(model)
+
+
+def test_sphere_against_wall_face(point):
+    """The Point's sphere 0.1 deep in the wall west of the start cell, the arrow pointing away from it."""
+    point.set_state([-1.6, 0.0, 0.0], [0, 0, 0])
+    point.forward([0, 0])
+    cons = point.contacts()
+    assert len(cons) == 1
+    c = cons[0]
+    assert c["dist"] == pytest.approx(-0.1, abs=1e-12)
+    assert np.allclose(c["frame"][0], [-1, 0, 0], atol=1e-12)           # from the sphere into the wall
+    assert np.allclose(c["pos"], [-2.05, 0.0, 0.5], atol=1e-12)         # midway between x = -2.1 (sphere) and x = -2 (wall)
+    assert (c["body1"], c["body2"]) == (0, -1)
+
+
+def test_sphere_just_outside_the_wall_is_no_contact(point):
+    point.set_state([-1.5 + 1e-9, 0.0, 0.0], [0, 0, 0])                 # the sphere's west pole 1e-9 short of the face, margin 0
+    point.forward([0, 0])
+    assert point.counts()["ncon"] == 0
+
+
+def test_box_face_against_wall_face(point):
+    """The arrow box head-on into the same wall, 0.05 deep: the four corners of its front face, all at the same depth."""
+    point.set_state([-0.95, 0.0, np.pi], [0, 0, 0])
+    point.forward([0, 0])
+    cons = point.contacts()
+    assert len(cons) == 4                                                # the sphere is 0.45 short of the wall
+    pts = sorted((round(c["pos"][1], 9), round(c["pos"][2], 9)) for c in cons)
+    assert pts == [(-0.1, 0.4), (-0.1, 0.6), (0.1, 0.4), (0.1, 0.6)]
+    for c in cons:
+        assert c["dist"] == pytest.approx(-0.05, abs=1e-9)
+        assert c["pos"][0] == pytest.approx(-2.025, abs=1e-9)            # midway between x = -2.05 (arrow) and x = -2 (wall)
+        assert np.allclose(c["frame"][0], [1, 0, 0], atol=1e-9)          # geom 1 = the wall (lower geom id), geom 2 = the arrow
+        assert (c["body1"], c["body2"]) == (-1, 0)
+
+
+def test_box_face_tilted_against_wall_face(point):
+    """The arrow yawed by 0.2 rad: its leading vertical edge enters first - two contacts, depth from the edge's x."""
+    th = np.pi - 0.2
+    x0 = -0.922
+    point.set_state([x0, 0.0, th], [0, 0, 0])
+    point.forward([0, 0])
+    cons = point.contacts()
+    # corners of the front face in the world: centre + R (0.5, +-0.1, .)
+    c, s = np.cos(th), np.sin(th)
+    cx, cy = x0 + 0.6 * c, 0.6 * s
+    corners = [(cx + 0.5 * c - sy * 0.1 * s, cy + 0.5 * s + sy * 0.1 * c) for sy in (-1, 1)]
+    deep = [p for p in corners if p[0] < -2.0]
+    assert len(deep) == 1 and len(cons) == 2                             # one vertical edge (two corners, z = 0.4 and 0.6) is inside
+    for k in cons:
+        assert k["dist"] == pytest.approx(deep[0][0] + 2.0, abs=1e-9)
+        assert k["pos"][1] == pytest.approx(deep[0][1], abs=1e-9)
+        assert np.allclose(k["frame"][0], [1, 0, 0], atol=1e-9)
+    assert sorted(round(k["pos"][2], 9) for k in cons) == [0.4, 0.6]
+
+
+def test_sphere_against_floor(oracle_lib):
+    """The Ant's torso sphere (r = 0.25) 0.05 deep in the floor: plane contact under its centre (geom 1 = the plane)."""
+    model = make_model("AntUMaze-v0")
+    o = oracle_lib.OracleEnv(model)
+    q = np.asarray(model.qpos0, float)[: int(model.nq)].copy()
+    q[0:3] = [0.3, -0.2, 0.2]
+    o.set_state(q, np.zeros(int(model.nv)))
+    o.forward(np.zeros(int(model.nu)))
+    under = [c for c in o.contacts() if np.allclose(c["pos"][:2], [0.3, -0.2], atol=1e-12)]
+    assert len(under) == 1
+    c = under[0]
+    assert c["dist"] == pytest.approx(-0.05, abs=1e-12)
+    assert np.allclose(c["frame"][0], [0, 0, 1], atol=1e-12)
+    assert c["pos"][2] == pytest.approx(-0.025, abs=1e-12)               # midway between the floor and the sphere's lowest point
+    assert (c["body1"], c["body2"]) == (-1, 0)
+
+
+def test_capsule_end_against_wall_face(oracle_lib):
+    """The Ant at its reference pose (legs stretched out horizontally at z = 0.75, ankle capsules r = 0.08 ending 0.8 out on
+    both diagonals, ant.xml:22-66) with the tips of its two west ankles 0.03 deep in the wall west of the start cell (east
+    face: x = -4): one contact per ankle at the end sphere - the other end of each capsule is 0.4 further from the wall."""
+    model = make_model("AntUMaze-v0")
+    assert float(model.cell_size) == 8.0
+    o = oracle_lib.OracleEnv(model)
+    q = np.asarray(model.qpos0, float)[: int(model.nq)].copy()
+    q[0] = -3.15
+    o.set_state(q, np.zeros(int(model.nv)))
+    o.forward(np.zeros(int(model.nu)))
+    cons = o.contacts()
+    assert len(cons) == 2
+    assert sorted(round(c["pos"][1], 9) for c in cons) == [-0.8, 0.8]
+    assert sorted(c["body1"] for c in cons) == [4, 6] and all(c["body2"] == -1 for c in cons)
+    for c in cons:
+        assert c["dist"] == pytest.approx(-0.03, abs=1e-9)
+        assert np.allclose(c["frame"][0], [-1, 0, 0], atol=1e-9)         # from the capsule into the wall
+        assert c["pos"][0] == pytest.approx(-4.015, abs=1e-9)            # midway between x = -4.03 (capsule) and x = -4 (wall)
+        assert c["pos"][2] == pytest.approx(0.75, abs=1e-9)
+
+
+def test_capsules_flat_on_the_floor(oracle_lib):
+    """The Ant at its reference pose lowered to z = 0.05: every leg capsule (r = 0.08) lies 0.03 deep in the floor and touches it
+    with BOTH end spheres, the torso sphere (r = 0.25) is 0.2 deep. Capsule ends along each diagonal: 0 and 0.2 (the hip stub
+    on the torso), 0.2 and 0.4 (the leg), 0.4 and 0.8 (the ankle)."""
+    model = make_model("AntUMaze-v0")
+    o = oracle_lib.OracleEnv(model)
+    q = np.asarray(model.qpos0, float)[: int(model.nq)].copy()
+    q[2] = 0.05
+    o.set_state(q, np.zeros(int(model.nv)))
+    o.forward(np.zeros(int(model.nu)))
+    cons = o.contacts()
+    assert o.counts()["overflow"] == 0
+    for c in cons:
+        assert np.allclose(c["frame"][0], [0, 0, 1], atol=1e-12) and c["body1"] == -1
+        assert c["pos"][2] == pytest.approx(0.5 * c["dist"], abs=1e-12)  # midway between the floor and the lowest point
+    sphere = [c for c in cons if abs(c["dist"] + 0.2) < 1e-9]
+    caps = [c for c in cons if abs(c["dist"] + 0.03) < 1e-9]
+    assert len(sphere) == 1 and len(caps) == len(cons) - 1 == 24
+    want = sorted((round(sx * r, 9), round(sy * r, 9)) for sx in (-1, 1) for sy in (-1, 1) for r in (0.0, 0.2, 0.2, 0.4, 0.4, 0.8))
+    got = sorted((round(c["pos"][0], 9) + 0.0, round(c["pos"][1], 9) + 0.0) for c in caps)
+    assert got == want
