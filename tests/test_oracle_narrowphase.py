@@ -132,3 +132,37 @@ def test_capsules_flat_on_the_floor(oracle_lib):
     want = sorted((round(sx * r, 9), round(sy * r, 9)) for sx in (-1, 1) for sy in (-1, 1) for r in (0.0, 0.2, 0.2, 0.4, 0.4, 0.8))
     got = sorted((round(c["pos"][0], 9) + 0.0, round(c["pos"][1], 9) + 0.0) for c in caps)
     assert got == want
+
+
+def test_contact_reference_acceleration_follows_the_documented_formula(point):
+    """MuJoCo's soft-constraint reference acceleration (documentation, "Solver parameters"): a_ref = -b v - k d(r) r with
+    b = 2 / (dmax tau), k = 1 / (dmax^2 tau^2 zeta^2), solref = (tau, zeta) = (0.02, 1) made safe as tau >= 2 timestep = 0.04,
+    and solimp mixed with equal weights between the two geoms: dmax = (0.99 [point.xml] + 0.95 [maze box default]) / 2; 0.1 deep
+    is far beyond the impedance width (0.001), so d(r) = dmax. All four pyramid rows of the contact share r and, for a
+    velocity along the normal, v."""
+    tau, zeta, dmax, r = 0.04, 1.0, 0.5 * (0.99 + 0.95), -0.1
+    k, b = 1.0 / (dmax ** 2 * tau ** 2 * zeta ** 2), 2.0 / (dmax * tau)
+    for vx in (0.0, -0.3, 0.2):
+        point.set_state([-1.6, 0.0, 0.0], [vx, 0, 0])
+        point.forward([0, 0])
+        J, D, aref, f = point.efc()
+        assert J.shape == (4, 3) and np.allclose(J[:, 0], 1.0)          # d(dist)/dt = +vx: the wall is to the west
+        assert np.allclose(aref, -b * vx - k * dmax * r, rtol=1e-12)
+        assert np.allclose(D, D[0]) and D[0] > 0                          # the four edges of the pyramid share their regularisation
+
+
+def test_contact_regularisation_follows_the_documented_formula(point):
+    """R of a pyramidal contact row as MuJoCo builds it (mj_makeImpedance, documentation "Solver parameters" / "Contact"):
+    R = 2 mu^2 R_first, R_first = (1 - d) / d * A with the approximate inverse inertia A = (1 + mu^2) (w_1 + w_2), w = the
+    translational body_invweight0 = trace(J M^-1 J^T) / 3 in the reference pose. The Point slides along x and y with its whole
+    mass m and cannot move along z: w = (1/m + 1/m + 0) / 3; the wall is the world (w = 0). D = 1 / R."""
+    model = make_model("PointUMaze-v0")
+    mass = float(np.asarray(model.body_mass)[0])
+    d, mu = 0.5 * (0.99 + 0.95), 1.0
+    w = 2.0 / (3.0 * mass)
+    R = 2.0 * mu * mu * (1.0 - d) / d * (1.0 + mu * mu) * w
+    point.set_state([-1.6, 0.0, 0.0], [0, 0, 0])
+    point.forward([0, 0])
+    assert point.contacts()[0]["mu"] == mu
+    _, D, _, _ = point.efc()
+    assert np.allclose(D, 1.0 / R, rtol=1e-9)
