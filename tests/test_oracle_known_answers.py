@@ -1,10 +1,11 @@
-"""Known answers for the narrow phase of the CPU restatement (oracle/mmz_oracle.c:400-647) in configurations whose contacts
+"""Known answers for the CPU restatement: its narrow phase (oracle/mmz_oracle.c:400-647) in configurations whose contacts
 follow from elementary geometry - the cases in which any correct narrow phase, MuJoCo's mjc_PlaneSphere / mjc_SphereBox /
 mjc_BoxBox included, must produce the same points: distance negative by the penetration, position midway between the two
 surfaces, normal from geom 1 to geom 2 (the conventions of mmz_narrow.cuh:1-8). Geometry of the scenes: the Point of
 assets/point.xml (sphere r = 0.5 at z = 0.5, arrow box 0.5 x 0.1 x 0.1 at 0.6 ahead) in the U maze of maze_task.py (cells of
 4, walls 2 high: the cell west of the start cell is a wall whose east face is the plane x = -2), the Ant's torso sphere
-(r = 0.25) over the floor."""
+(r = 0.25) over the floor. The last tests evaluate MuJoCo's documented formulas for the reference acceleration and the
+regularisation of contact and joint-limit rows independently and compare."""
 import numpy as np
 import pytest
 
@@ -166,3 +167,32 @@ def test_contact_regularisation_follows_the_documented_formula(point):
     assert point.contacts()[0]["mu"] == mu
     _, D, _, _ = point.efc()
     assert np.allclose(D, 1.0 / R, rtol=1e-9)
+
+
+def test_joint_limit_rows_follow_the_documented_formulas(oracle_lib):
+    """The Ant in its reference pose, high above the floor: its four ankle hinges sit at 0, outside their ranges (ant.xml:
+    [30, 70] or [-70, -30] degrees), so exactly four limit rows are active, 0.5236 rad deep. Row: J = +1 at a violated lower
+    limit, -1 at an upper one; a_ref = k d |r| with tau = 2 timestep (solref made safe), d = dmax = 0.95 (far beyond the
+    impedance width); R = (1 - d) / d * dof_invweight0 with dof_invweight0 = (M^-1)_dd in the reference pose (hinges)."""
+    model = make_model("AntUMaze-v0")
+    nq, nv = int(model.nq), int(model.nv)
+    o = oracle_lib.OracleEnv(model)
+    q = np.asarray(model.qpos0, float)[:nq].copy()
+    q[2] = 3.0
+    o.set_state(q, np.zeros(nv))
+    o.forward(np.zeros(int(model.nu)))
+    assert o.counts()["ncon"] == 0
+    J, D, aref, _ = o.efc()
+    assert J.shape == (4, nv)
+    rng_ = np.asarray(model.jnt_range, float)
+    Minv = np.linalg.inv(o.mass_matrix())
+    tau, d, depth = 2 * float(model.timestep), 0.95, np.deg2rad(30.0)
+    k = 1.0 / (d * d * tau * tau)
+    for row, dof in enumerate((7, 9, 11, 13)):
+        jnt = dof - 5                                                    # joint 0 is the free joint (dofs 0..5)
+        lower = rng_[jnt][0] > 0                                         # range above 0: the LOWER limit is violated
+        want = np.zeros(nv)
+        want[dof] = 1.0 if lower else -1.0
+        assert np.allclose(J[row], want)
+        assert aref[row] == pytest.approx(k * d * depth, rel=1e-6)
+        assert D[row] == pytest.approx(1.0 / ((1 - d) / d * Minv[dof, dof]), rel=1e-6)
