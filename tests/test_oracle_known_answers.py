@@ -196,3 +196,39 @@ def test_joint_limit_rows_follow_the_documented_formulas(oracle_lib):
         assert np.allclose(J[row], want)
         assert aref[row] == pytest.approx(k * d * depth, rel=1e-6)
         assert D[row] == pytest.approx(1.0 / ((1 - d) / d * Minv[dof, dof]), rel=1e-6)
+
+
+def test_actuation_passive_and_bias_forces_of_the_ant_in_known_states(oracle_lib):
+    """Smooth forces from first principles. ant.xml:8,23,71-78: motors (gear 1) on the eight hinges in the order hip_4, ankle_4,
+    hip_1, ankle_1, ... with ctrlrange [-30, 30] (clamped), joint damping 1 and armature 1 on every hinge, none on the free
+    joint. (1) actuation = clip(ctrl) on the motor's dof; (2) passive = -damping * qvel on the hinges, nothing on the free
+    joint; (3) at rest the bias force is gravity alone: total mass * 9.81 along the free joint's z, no net torque on the
+    torso in the symmetric reference pose; (4) the free joint's translations carry the whole mass, a hinge its armature plus
+    the inertia of what hangs on it."""
+    model = make_model("AntUMaze-v0")
+    nq, nv, nu = int(model.nq), int(model.nv), int(model.nu)
+    o = oracle_lib.OracleEnv(model)
+    q = np.asarray(model.qpos0, float)[:nq].copy()
+    q[2] = 3.0
+    ctrl = np.array([5.0, -2.5, 30.0, -30.0, 45.0, -70.0, 0.0, 1.0])  # two of them outside the control range
+    v = np.zeros(nv)
+    v[6:] = np.linspace(-1.0, 1.0, 8)
+    o.set_state(q, v)
+    o.forward(ctrl)
+    act = o.vec("qfrc_act")
+    want = np.zeros(nv)
+    # dofs 6..13 = hip_1, ankle_1, hip_2, ankle_2, hip_3, ankle_3, hip_4, ankle_4 (body order); motors start at hip_4
+    for k, dof in enumerate((12, 13, 6, 7, 8, 9, 10, 11)):
+        want[dof] = np.clip(ctrl[k], -30.0, 30.0)
+    assert np.allclose(act, want)
+    pas = o.vec("qfrc_passive")
+    assert np.allclose(pas[:6], 0) and np.allclose(pas[6:], -1.0 * v[6:])
+    o.set_state(q, np.zeros(nv))
+    o.forward(np.zeros(nu))
+    bias = o.vec("qfrc_bias")
+    mass = float(np.asarray(model.body_mass)[: int(model.nbody)].sum())
+    assert bias[2] == pytest.approx(mass * 9.81, rel=1e-12)
+    assert np.allclose(bias[:2], 0, atol=1e-12) and np.allclose(bias[3:6], 0, atol=1e-9)
+    M = o.mass_matrix()
+    assert np.allclose(np.diag(M)[:3], mass)
+    assert np.all(np.diag(M)[6:] > 1.0)
